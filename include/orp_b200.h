@@ -1,0 +1,163 @@
+/*
+ * orp_b200.h - C ABI of liborp_b200.so: the B200 (sm_100a) implementation of the
+ * OrientedRepPoints dense-inference hot path.
+ *
+ * Plain pointers and sizes only - no torch types.  Every entry point cites the reference
+ * interface it replaces.  Two families:
+ *
+ *   *_host   : host buffers in / host buffers out, blocking - drop-in for the reference's
+ *              own C entry points that Cython binds (DOTA_devkit/poly_nms_gpu/*.hpp).
+ *   (others) : DEVICE pointers, asynchronous on `stream` (a cudaStream_t passed as void*),
+ *              what the reference's pybind11 torch extensions (mmdet/ops/.../src/*_cuda.cpp)
+ *              do with at::Tensor::data_ptr().  Scratch memory comes from the CUDA
+ *              stream-ordered pool (cudaMallocAsync) of the current device.
+ *
+ * All functions return 0 on success, a negative ORP_E* code otherwise; orp_last_error()
+ * gives the message (thread-local).  There is no CPU fallback anywhere in this library.
+ */
+#ifndef ORP_B200_H_
+#define ORP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORP_OK 0
+#define ORP_EINVAL (-1)   /* bad argument                                  */
+#define ORP_ECUDA (-2)    /* CUDA runtime error (see orp_last_error)        */
+#define ORP_ENOGPU (-3)   /* no sm_100 device / wrong architecture          */
+#define ORP_EOVERFLOW (-4) /* internal capacity exceeded after retries       */
+
+const char *orp_last_error(void);
+/* library/ABI version (major*100+minor) and the SM architecture it was compiled for (100) */
+int orp_version(void);
+int orp_compiled_sm(void);
+/* number of kernel launches issued by this library since load / since the last reset
+ * (bench.py reports it as "gpu_launches") */
+int64_t orp_launch_count(void);
+void orp_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Rotated / polygon NMS
+ * ---------------------------------------------------------------------------------------- */
+
+/* IoU arithmetic used to decide `iou > thr`:
+ *   ORP_NMS_EXACT64  candidate pairs from an exact-safe AABB sweep; fp32 convex clipping in
+ *                    pair-local coordinates with a proven error band; pairs inside the band are
+ *                    re-evaluated with the reference's fp64 algorithm (DOTA_devkit/polyiou.cpp)
+ *                    so every decision equals the fp64 reference decision.  Default.
+ *   ORP_NMS_COMPAT32 the reference's fp32 arithmetic (mmdet/ops/nms/src/rnms_kernel.cu:17-147),
+ *                    origin-anchored triangle fan, every pair of the upper triangle evaluated,
+ *                    no operation contracted - bit-identical to mmdet/ops/nms/src/rnms_cpu.cpp.
+ */
+#define ORP_NMS_EXACT64 0
+#define ORP_NMS_COMPAT32 1
+
+/* degenerate-union convention:
+ *   ORP_UNION_NAN_KEEPS      rnms  (rnms_kernel.cu:131-147: 0/0 = NaN, `NaN > thr` false)
+ *   ORP_UNION_GUARD          poly_gpu_nms (poly_nms_kernel.cu:205-210: (inter+1)/(union+1))
+ *   ORP_UNION_NAN_SUPPRESSES py_cpu_nms_poly (ResultMerge.py:39 keeps only `iou <= thr`)
+ */
+#define ORP_UNION_NAN_KEEPS 0
+#define ORP_UNION_GUARD 1
+#define ORP_UNION_NAN_SUPPRESSES 2
+
+/* output ordering of the kept indices:
+ *   ORP_ORDER_INDEX_ASC  rnms_cuda (rnms_kernel.cu:261-264)
+ *   ORP_ORDER_SCORE_DESC poly_gpu_nms (poly_nms.pyx:19-24), py_cpu_nms_poly (ResultMerge.py:28-41)
+ */
+#define ORP_ORDER_INDEX_ASC 0
+#define ORP_ORDER_SCORE_DESC 1
+
+/* Greedy rotated NMS over n quadrilaterals, optionally segmented.
+ *   dets      device float32 [n, 9] rows (x1,y1,x2,y2,x3,y3,x4,y4,score), row stride 9
+ *   segments  device int32 [n] or NULL: boxes only interact inside one segment (class id for
+ *             multiclass_rnms - replaces the coordinate-offset trick of
+ *             mmdet/core/post_processing/bbox_nms.py:156-158; (image,class) id for ResultMerge)
+ *   keep_out  device int64 [n]: kept original row indices, in `order`
+ *   num_out   device int32 [1]: number kept
+ * Replaces rnms_cuda() (mmdet/ops/nms/src/rnms_kernel.cu:204-265, bound at
+ * mmdet/ops/nms/src/rnms_cuda.cpp:8-17).  Ties in score: lower row index first.
+ * iou_thr is a double because the fp64 reference compares against a Python float
+ * (ResultMerge.py:39); COMPAT32 rounds it to fp32 like rnms_cuda's `float nms_overlap_thresh`.
+ * Asynchronous; nothing is copied to the host (one exception: if the suppression-edge list
+ * outgrows its first allocation the call synchronises once and retries with the exact size). */
+int orp_rnms(const float *dets, const int32_t *segments, int n, double iou_thr, int iou_mode,
+             int union_mode, int order, int64_t *keep_out, int32_t *num_out, void *stream);
+
+/* Drop-in for `void _poly_nms(int* keep_out, int* num_out, const float* polys_host,
+ * int polys_num, int polys_dim, float nms_overlap_thresh, int device_id)`
+ * (DOTA_devkit/poly_nms_gpu/poly_nms.hpp:9-10).  polys_host must ALREADY be sorted by score
+ * descending as poly_nms.pyx:19-21 does; keep_out receives positions in that order.
+ * Host buffers, blocking.  polys_dim must be 9.  Unlike the reference, device_id is honoured. */
+int orp_poly_nms_host(int *keep_out, int *num_out, const float *polys_host, int polys_num,
+                      int polys_dim, float nms_overlap_thresh, int device_id);
+
+/* Statistics of the last orp_rnms call on this thread: candidate pairs that passed the AABB
+ * sweep, pairs clipped, pairs sent to the fp64 re-evaluation, suppression edges, rounds of the
+ * greedy resolution.  Requires the stream to be synchronised by the caller first. */
+typedef struct {
+    int64_t pairs_total;     /* n(n-1)/2 within segments is NOT computed; this is the sweep count */
+    int64_t pairs_aabb;      /* pairs whose axis-aligned hulls overlap                            */
+    int64_t pairs_clipped;   /* pairs that reached the polygon clip                              */
+    int64_t pairs_fp64;      /* pairs decided by the fp64 reference algorithm                    */
+    int64_t edges;           /* pairs with iou > thr                                             */
+    int32_t rounds;          /* resolution rounds                                                */
+    int32_t n;
+} orp_nms_stats;
+int orp_rnms_last_stats(orp_nms_stats *out);
+
+/* ------------------------------------------------------------------------------------------
+ * Pairwise rotated IoU
+ * ---------------------------------------------------------------------------------------- */
+
+/* Drop-in for `void _overlaps(float* overlaps, const float* boxes, const float* query_boxes,
+ * int n, int k, int device_id)` (DOTA_devkit/poly_nms_gpu/poly_overlaps.hpp:1): (cx,cy,w,h,theta)
+ * boxes -> corners as RotBox2Poly (poly_overlaps_kernel.cu:280-297) -> N x K IoU with the
+ * zero-union guard (:300-328).  Host buffers, blocking. */
+int orp_poly_overlaps_host(float *overlaps, const float *boxes, const float *query_boxes, int n,
+                           int k, int device_id);
+/* same on device pointers, asynchronous */
+int orp_poly_overlaps(const float *boxes5, int n, const float *query5, int k, float *out,
+                      void *stream);
+
+/* N x K IoU of quadrilaterals (8 coords each), device pointers.  mode ORP_NMS_EXACT64 gives
+ * fp32 values within 1e-5 of DOTA_devkit/polyiou.cpp (uncertain pairs recomputed in fp64);
+ * ORP_NMS_COMPAT32 gives rnms_kernel.cu:131-147 bit-for-bit. */
+int orp_quad_iou_matrix(const float *quads_a, int n, const float *quads_b, int k, int iou_mode,
+                        int union_mode, float *out, void *stream);
+
+/* fp64 IoU of aligned pairs with the algorithm and arithmetic of iou_poly()
+ * (DOTA_devkit/polyiou.cpp:108-128) - the batched device equivalent of the SWIG call. */
+int orp_iou_poly_f64_pairs(const double *p8, const double *q8, int n, double *out, void *stream);
+
+/* detectron2-style rotated boxes (cx,cy,w,h,theta in RADIANS as modified at
+ * mmdet/ops/box_iou_rotated/src/box_iou_rotated_utils.h:59-62) -> N x M IoU; replaces
+ * box_iou_rotated_cuda (box_iou_rotated_cuda.cu:13-62). */
+int orp_box_iou_rotated(const float *boxes1, int n, const float *boxes2, int m, float *out,
+                        void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * minaerarect
+ * ---------------------------------------------------------------------------------------- */
+
+/* 9-point sets -> minimum-area rectangles.  Replaces minareabbox_cuda()
+ * (mmdet/ops/minarearect/src/minarearect_kernel.cu:470-505, bound at minarearect_cuda.cpp:5-13).
+ *   pts       device float32 [n,18] rows (x0,y0,...,x8,y8), contiguous
+ *   out       device float32 [n,8] corners (xmax,ymin),(xmin,ymin),(xmin,ymax),(xmax,ymax) of the
+ *             winning rotated frame mapped back (kernel.cu:380-450)
+ *   hull_map  device int32 [n,9] or NULL: hull vertex -> input point index, -1 padded
+ *             (points_to_convex_ind, kernel.cu:330-340)
+ *   scale, center: if center != NULL the fused affine of orientedreppoints_head.py:748-749 is
+ *             applied: out = rect*scale + (center[2i],center[2i+1]) repeated 4 times; center is
+ *             device float32 [n,2].  Pass scale=1, center=NULL for the bare op.
+ * Asynchronous, output stays on the device (the reference copies through the host). */
+int orp_minarearect(const float *pts, int n, float *out, int32_t *hull_map, float scale,
+                    const float *center, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORP_B200_H_ */

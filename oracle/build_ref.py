@@ -1,0 +1,83 @@
+"""Compile the reference's own CPU sources of the path into oracle/_ref/ (TEST INFRASTRUCTURE).
+
+Sources are compiled FROM WHERE THEY LIE under /root/reference (nothing is copied into the
+repo; oracle/_ref/ is git-ignored but travels to the GPU box with the gpurun snapshot).
+
+  libref_polyiou.so   DOTA_devkit/polyiou.cpp  (+ oracle/ref_harness_polyiou.cpp, C ABI re-export)
+  _polyiou<EXT>.so    DOTA_devkit/polyiou_wrap.cxx + polyiou.cpp  (the reference's SWIG module;
+                      polyiou.py is copied next to it as a build OUTPUT so `import polyiou` works)
+  ref_rnms_cpu.so     mmdet/ops/nms/src/rnms_cpu.cpp unmodified (+ oracle/ref_harness_rnms.cpp)
+  ref_box_iou_rotated.so  mmdet/ops/box_iou_rotated/src/box_iou_rotated_cpu.cpp unmodified
+
+Only runs where /root/reference exists (the authoring container).  The reference's CUDA
+sources (mmdet/ops/**/src/*.cu) are NOT buildable: they include THC/THC.h which torch 2.11
+no longer ships - stated in DESIGN.md.
+"""
+import os
+import shutil
+import subprocess
+import sys
+import sysconfig
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+REF = os.environ.get("ORP_REFERENCE_ROOT", "/root/reference")
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+
+
+def _stale(target, deps):
+    return (not os.path.exists(target)) or any(os.path.getmtime(target) < os.path.getmtime(d) for d in deps)
+
+
+def build(verbose=False, with_torch=True):
+    if not os.path.isdir(REF):
+        return None
+    os.makedirs(OUT, exist_ok=True)
+    devkit = os.path.join(REF, "DOTA_devkit")
+    # 1. polyiou.cpp behind a C ABI
+    lib = os.path.join(OUT, "libref_polyiou.so")
+    harness = os.path.join(HERE, "ref_harness_polyiou.cpp")
+    src = os.path.join(devkit, "polyiou.cpp")
+    if _stale(lib, [harness, src]):
+        _run(["g++", "-O2", "-shared", "-fPIC", "-w", '-DREF_POLYIOU_CPP="%s"' % src, harness, "-o", lib], verbose)
+    # 2. the SWIG module exactly as the reference ships it (checked-in wrapper, no swig needed)
+    ext = sysconfig.get_config_var("EXT_SUFFIX")
+    swig = os.path.join(OUT, "_polyiou" + ext)
+    wrap = os.path.join(devkit, "polyiou_wrap.cxx")
+    if _stale(swig, [wrap, src]):
+        _run(["g++", "-O2", "-shared", "-fPIC", "-w", "-I" + sysconfig.get_paths()["include"],
+              "-I" + devkit, wrap, src, "-o", swig], verbose)
+        shutil.copyfile(os.path.join(devkit, "polyiou.py"), os.path.join(OUT, "polyiou.py"))
+    if not with_torch:
+        return OUT
+    # 3./4. torch CPU extensions, reference sources unmodified
+    import torch  # noqa: F401
+    from torch.utils import cpp_extension as ce
+    inc = []
+    for p in ce.include_paths():
+        inc += ["-isystem", p]
+    inc += ["-I" + sysconfig.get_paths()["include"]]
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    common = ["g++", "-O2", "-shared", "-fPIC", "-w", "-std=c++17",
+              "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)] + inc
+    link = ["-L" + tlib, "-Wl,-rpath," + tlib, "-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python"]
+    rn = os.path.join(OUT, "ref_rnms_cpu.so")
+    rsrc = os.path.join(REF, "mmdet/ops/nms/src/rnms_cpu.cpp")
+    rh = os.path.join(HERE, "ref_harness_rnms.cpp")
+    if _stale(rn, [rsrc, rh]):
+        _run(common + ["-DTORCH_EXTENSION_NAME=ref_rnms_cpu", rsrc, rh, "-o", rn] + link, verbose)
+    bi = os.path.join(OUT, "ref_box_iou_rotated.so")
+    bsrc = os.path.join(REF, "mmdet/ops/box_iou_rotated/src/box_iou_rotated_cpu.cpp")
+    bh = os.path.join(HERE, "ref_harness_box_iou_rotated.cpp")
+    if os.path.exists(bh) and _stale(bi, [bsrc, bh]):
+        _run(common + ["-I" + os.path.dirname(bsrc), bsrc, bh, "-o", bi] + link, verbose)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(verbose=True))

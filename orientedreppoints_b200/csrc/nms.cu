@@ -1,0 +1,647 @@
+// nms.cu - rotated / polygon greedy NMS for sm_100a.
+//
+// Replaces rnms_cuda (mmdet/ops/nms/src/rnms_kernel.cu:204-265) and _poly_nms
+// (DOTA_devkit/poly_nms_gpu/poly_nms_kernel.cu:277-329).  The reference materialises an
+// N x N/64 bit matrix (1.25 GB at N = 100k), copies it to the host and scans it there.  Here:
+//
+//   prep     per box: AABB, validity, score key                                   (1 pass, 36 B/box)
+//   sort     CUB radix sorts: by score (rank) and by (segment, xmin) (sweep order)
+//   sweep    one warp per box walks its x-interval in the xmin-sorted arrays, lanes test AABBs
+//            (coalesced float4), survivors are compacted into a per-warp shared-memory queue and
+//            clipped 32 at a time (fp32 Sutherland-Hodgman in pair-local coordinates; fp64
+//            reference algorithm inside the error band) -> sparse list of suppression edges
+//   csr      in-degree scan + scatter: for every box the better-ranked boxes overlapping it
+//   resolve  cooperative kernel iterating  keep(i) <=> all in-neighbours suppressed,
+//            suppressed(i) <=> some in-neighbour kept  to its (unique) fixed point = greedy NMS
+//   select   CUB flagged select into the caller's int64 buffer, count stays on the device
+//
+// Nothing touches the host; no N^2 memory.
+#include <cooperative_groups.h>
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+#include "geom.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace orp {
+
+struct NmsCounters {
+    unsigned long long pairs_swept, pairs_aabb, pairs_clipped, pairs_fp64, edges;
+    int overflow;
+    int rounds;
+};
+
+static thread_local orp_nms_stats g_last_stats;
+static thread_local NmsCounters *g_stats_dev = nullptr;   // device copy of the last call
+static thread_local NmsCounters *g_stats_pinned = nullptr;
+
+__device__ __forceinline__ uint32_t orderable(float f)
+{
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // ascending order == ascending float
+}
+
+// ---------------------------------------------------------------------------------------------
+// prep: keys for the two sorts
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nms_prep_kernel(const float *__restrict__ dets, const int32_t *__restrict__ segments, int n,
+                uint32_t *__restrict__ score_key, uint64_t *__restrict__ sweep_key,
+                int32_t *__restrict__ iota)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *d = dets + (size_t)i * 9;
+    float x[4], y[4];
+    bool finite = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        x[k] = d[2 * k]; y[k] = d[2 * k + 1];
+        finite = finite && isfinite(x[k]) && isfinite(y[k]);
+    }
+    float xmin = fminf(fminf(x[0], x[1]), fminf(x[2], x[3]));
+    score_key[i] = ~orderable(d[8]);                       // ascending key == descending score
+    uint32_t seg = segments ? (uint32_t)segments[i] : 0u;
+    // non-finite boxes go to the very end of the sweep order and never take part in it
+    uint64_t key = finite ? (((uint64_t)(seg & 0x7FFFFFFFu) << 32) | orderable(xmin)) : ~0ull;
+    sweep_key[i] = key;
+    iota[i] = i;
+}
+
+__global__ void __launch_bounds__(256)
+nms_rank_kernel(const int32_t *__restrict__ order, int n, int32_t *__restrict__ rank)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) rank[order[r]] = r;
+}
+
+// gather boxes into structure-of-arrays in `perm` order
+__global__ void __launch_bounds__(256)
+nms_gather_kernel(const float *__restrict__ dets, const int32_t *__restrict__ segments,
+                  const int32_t *__restrict__ perm, const uint64_t *__restrict__ sorted_key,
+                  const int32_t *__restrict__ rank, int n, float4 *__restrict__ aabb,
+                  float4 *__restrict__ v01, float4 *__restrict__ v23, int32_t *__restrict__ rk,
+                  int32_t *__restrict__ sg, float *__restrict__ area, int32_t *__restrict__ nvalid)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int i = perm[s];
+    const float *d = dets + (size_t)i * 9;
+    float c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c[k] = d[k];
+    float xmin = fminf(fminf(c[0], c[2]), fminf(c[4], c[6]));
+    float xmax = fmaxf(fmaxf(c[0], c[2]), fmaxf(c[4], c[6]));
+    float ymin = fminf(fminf(c[1], c[3]), fminf(c[5], c[7]));
+    float ymax = fmaxf(fmaxf(c[1], c[3]), fmaxf(c[5], c[7]));
+    aabb[s] = make_float4(xmin, ymin, xmax, ymax);
+    v01[s] = make_float4(c[0], c[1], c[2], c[3]);
+    v23[s] = make_float4(c[4], c[5], c[6], c[7]);
+    rk[s] = rank[i];
+    sg[s] = segments ? segments[i] : 0;
+    // area about the box's own first vertex (small coordinates -> accurate)
+    float ux = c[2] - c[0], uy = c[3] - c[1], vx = c[4] - c[0], vy = c[5] - c[1];
+    float wx = c[6] - c[0], wy = c[7] - c[1];
+    // negative marks "not a convex quadrilateral": such boxes are never pruned by the area bound and
+    // are always decided by the fp64 reference algorithm (which accepts arbitrary quadrilaterals)
+    area[s] = quad_is_convex(c) ? 0.5f * fabsf((ux * vy - uy * vx) + (vx * wy - vy * wx)) : -1.0f;
+    bool valid = sorted_key ? (sorted_key[s] != ~0ull) : true;
+    // first invalid position = number of valid boxes (keys are sorted, invalid ones last)
+    if (sorted_key) {
+        bool prev_valid = (s == 0) ? true : (sorted_key[s - 1] != ~0ull);
+        if (!valid && prev_valid) *nvalid = s;
+        if (valid && s == n - 1) *nvalid = n;
+    } else if (s == 0) {
+        *nvalid = n;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pair decision
+// ---------------------------------------------------------------------------------------------
+struct Quad { float c[8]; };
+
+__device__ __noinline__ bool decide_fp64(const Quad &A, const Quad &B, double thr, int union_mode)
+{
+    double p[8], q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { p[k] = (double)A.c[k]; q[k] = (double)B.c[k]; }
+    PairRes<double> r = ref_quad_pair<double>(p, q);
+    double iou = iou_from<double>(r, union_mode);
+    return suppresses<double>(iou, thr, union_mode);
+}
+
+// returns true iff the reference's fp64 IoU of (A,B) suppresses at thr
+__device__ __forceinline__ bool decide_exact(const Quad &A, const Quad &B, const float4 &ba,
+                                             const float4 &bb, bool both_convex, double thr,
+                                             int union_mode, bool &used64)
+{
+    if (!both_convex) {
+        used64 = true;
+        return decide_fp64(A, B, thr, union_mode);
+    }
+    const float ox = 0.5f * (fmaxf(ba.x, bb.x) + fminf(ba.z, bb.z));
+    const float oy = 0.5f * (fmaxf(ba.y, bb.y) + fminf(ba.w, bb.w));
+    float a[8], b[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a[2 * k] = A.c[2 * k] - ox; a[2 * k + 1] = A.c[2 * k + 1] - oy;
+        b[2 * k] = B.c[2 * k] - ox; b[2 * k + 1] = B.c[2 * k + 1] - oy;
+    }
+    FastRes r = fast_quad_pair(a, b);
+    const float t = (float)thr;
+    const float margin = r.inter * (1.f + t) - t * (r.area_a + r.area_b);
+    const float band = 4.f * r.err + 1e-6f * (r.area_a + r.area_b);
+    used64 = false;
+    if (fabsf(margin) > band) return margin > 0.f;
+    used64 = true;
+    return decide_fp64(A, B, thr, union_mode);
+}
+
+struct SweepParams {
+    const float4 *aabb, *v01, *v23;
+    const int32_t *rk, *sg;
+    const float *area;
+    const int32_t *nvalid;
+    int2 *edges;
+    int32_t *indeg;
+    unsigned long long edge_cap;
+    NmsCounters *ctr;
+    double thr;
+    int union_mode;
+};
+
+constexpr int kSweepWarps = 8;
+
+__global__ void __launch_bounds__(kSweepWarps * 32)
+nms_sweep_kernel(SweepParams P)
+{
+    __shared__ int32_t queue[kSweepWarps][64];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nv = *P.nvalid;
+    const int nwarps = gridDim.x * kSweepWarps;
+    unsigned long long c_swept = 0, c_aabb = 0, c_clip = 0, c_64 = 0, c_edge = 0;
+    const float thrf = (float)P.thr;
+
+    for (int i = blockIdx.x * kSweepWarps + wib; i < nv; i += nwarps) {
+        const float4 ba = P.aabb[i];
+        const int seg_i = P.sg[i];
+        const int rk_i = P.rk[i];
+        const float area_i = P.area[i];
+        Quad A;
+        {
+            float4 t0 = P.v01[i], t1 = P.v23[i];
+            A.c[0] = t0.x; A.c[1] = t0.y; A.c[2] = t0.z; A.c[3] = t0.w;
+            A.c[4] = t1.x; A.c[5] = t1.y; A.c[6] = t1.z; A.c[7] = t1.w;
+        }
+        int qn = 0;
+        bool more = true;
+        for (int base = i + 1; more || qn > 0; base += 32) {
+            bool hit = false;
+            int j = base + lane;
+            if (more) {
+                bool cont = false;
+                if (j < nv) {
+                    const float4 bb = P.aabb[j];
+                    cont = (P.sg[j] == seg_i) && (bb.x <= ba.z);
+                    if (cont) {
+                        ++c_swept;
+                        hit = (bb.x < ba.z) && (bb.y < ba.w) && (bb.w > ba.y);
+                        if (hit) {
+                            ++c_aabb;
+                            // exact-safe area bound: inter <= min(area_i, area_j, |AABB_i ^ AABB_j|)
+                            const float iw = fminf(ba.z, bb.z) - fmaxf(ba.x, bb.x);
+                            const float ih = fminf(ba.w, bb.w) - fmaxf(ba.y, bb.y);
+                            const float area_j = P.area[j];
+                            const float imax = fminf(fminf(area_i, area_j), iw * ih);
+                            // iou <= imax / (ai + aj - imax); prune when clearly below thr
+                            if (imax * (1.f + thrf) < 0.999f * thrf * (area_i + area_j) && imax > 0.f) hit = false;
+                        }
+                    }
+                }
+                more = __all_sync(0xffffffffu, cont);
+            }
+            const unsigned hm = __ballot_sync(0xffffffffu, hit);
+            if (hit) queue[wib][qn + __popc(hm & ((1u << lane) - 1u))] = j;
+            qn += __popc(hm);
+            __syncwarp();
+            // drain when full enough, or completely once the sweep is over
+            while (qn >= 32 || (!more && qn > 0)) {
+                const int take = qn < 32 ? qn : 32;
+                const int slot = qn - take + lane;
+                bool edge = false;
+                int lo = 0, hi = 0;
+                if (lane < take) {
+                    const int jj = queue[wib][slot];
+                    Quad B;
+                    float4 t0 = P.v01[jj], t1 = P.v23[jj];
+                    B.c[0] = t0.x; B.c[1] = t0.y; B.c[2] = t0.z; B.c[3] = t0.w;
+                    B.c[4] = t1.x; B.c[5] = t1.y; B.c[6] = t1.z; B.c[7] = t1.w;
+                    const float4 bb = P.aabb[jj];
+                    bool used64;
+                    ++c_clip;
+                    edge = decide_exact(A, B, ba, bb, area_i >= 0.f && P.area[jj] >= 0.f, P.thr, P.union_mode, used64);
+                    c_64 += used64;
+                    const int rk_j = P.rk[jj];
+                    lo = rk_i > rk_j ? rk_i : rk_j;   // worse-ranked box is the one suppressed
+                    hi = rk_i > rk_j ? rk_j : rk_i;
+                }
+                const unsigned em = __ballot_sync(0xffffffffu, edge);
+                if (em) {
+                    unsigned long long basep = 0;
+                    if (lane == 0) basep = atomicAdd(&P.ctr->edges, (unsigned long long)__popc(em));
+                    basep = __shfl_sync(0xffffffffu, basep, 0);
+                    if (edge) {
+                        unsigned long long pos = basep + __popc(em & ((1u << lane) - 1u));
+                        if (pos < P.edge_cap) {
+                            P.edges[pos] = make_int2(lo, hi);
+                            atomicAdd(&P.indeg[lo], 1);
+                        } else {
+                            P.ctr->overflow = 1;
+                        }
+                        ++c_edge;
+                    }
+                }
+                qn -= take;
+                __syncwarp();
+            }
+            if (!more && qn == 0) break;
+        }
+    }
+    // one atomic per warp per counter
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c_swept += __shfl_down_sync(0xffffffffu, c_swept, o);
+        c_aabb += __shfl_down_sync(0xffffffffu, c_aabb, o);
+        c_clip += __shfl_down_sync(0xffffffffu, c_clip, o);
+        c_64 += __shfl_down_sync(0xffffffffu, c_64, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&P.ctr->pairs_swept, c_swept);
+        atomicAdd(&P.ctr->pairs_aabb, c_aabb);
+        atomicAdd(&P.ctr->pairs_clipped, c_clip);
+        atomicAdd(&P.ctr->pairs_fp64, c_64);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// COMPAT32: every pair of the upper triangle with the reference's fp32 arithmetic
+// (rnms_kernel.cu:149-201: 64 x 64 tiles, column boxes staged in shared memory)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+nms_compat_tiles_kernel(const float4 *__restrict__ v01, const float4 *__restrict__ v23,
+                        const int32_t *__restrict__ sg, int n, float thr, int union_mode,
+                        int2 *edges, int32_t *indeg, unsigned long long edge_cap, NmsCounters *ctr)
+{
+    // linear upper-triangle tile index -> (rb, cb), cb >= rb
+    const int nb = (n + 63) / 64;
+    long long t = blockIdx.x;
+    int rb = 0;
+    {
+        // row rb has (nb - rb) tiles; solve by a short loop on one thread, broadcast via smem
+        __shared__ int s_rb, s_cb;
+        if (threadIdx.x == 0) {
+            long long rem = t;
+            int r = 0;
+            // closed form start then fix up
+            double nbd = (double)nb;
+            r = (int)floor(((2.0 * nbd + 1.0) - sqrt((2.0 * nbd + 1.0) * (2.0 * nbd + 1.0) - 8.0 * (double)t)) * 0.5);
+            if (r < 0) r = 0;
+            if (r >= nb) r = nb - 1;
+            auto start = [&](int rr) { return (long long)rr * nb - (long long)rr * (rr - 1) / 2; };
+            while (r > 0 && start(r) > t) --r;
+            while (r + 1 < nb && start(r + 1) <= t) ++r;
+            rem = t - start(r);
+            s_rb = r;
+            s_cb = r + (int)rem;
+        }
+        __syncthreads();
+        rb = s_rb;
+        t = s_cb;
+    }
+    const int cb = (int)t;
+    __shared__ float col[64][8];
+    __shared__ int colseg[64];
+    const int cj = cb * 64 + threadIdx.x;
+    if (cj < n) {
+        float4 a = v01[cj], b = v23[cj];
+        col[threadIdx.x][0] = a.x; col[threadIdx.x][1] = a.y; col[threadIdx.x][2] = a.z; col[threadIdx.x][3] = a.w;
+        col[threadIdx.x][4] = b.x; col[threadIdx.x][5] = b.y; col[threadIdx.x][6] = b.z; col[threadIdx.x][7] = b.w;
+        colseg[threadIdx.x] = sg[cj];
+    }
+    __syncthreads();
+    const int ri = rb * 64 + threadIdx.x;
+    if (ri >= n) return;
+    float p[8];
+    {
+        float4 a = v01[ri], b = v23[ri];
+        p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
+    }
+    const int seg_i = sg[ri];
+    const int ncol = min(64, n - cb * 64);
+    const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+    unsigned long long clipped = 0;
+    for (int c = start; c < ncol; ++c) {
+        if (colseg[c] != seg_i) continue;
+        float q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) q[k] = col[c][k];
+        PairRes<float> r = ref_quad_pair<float>(p, q);
+        float iou = iou_from<float>(r, union_mode);
+        ++clipped;
+        if (suppresses<float>(iou, thr, union_mode)) {
+            unsigned long long pos = atomicAdd(&ctr->edges, 1ull);
+            if (pos < edge_cap) {
+                const int lo = cb * 64 + c, hi = ri;   // arrays are in rank order: row is better
+                edges[pos] = make_int2(lo, hi);
+                atomicAdd(&indeg[lo], 1);
+            } else {
+                ctr->overflow = 1;
+            }
+        }
+    }
+    atomicAdd(&ctr->pairs_clipped, clipped);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSR scatter + greedy resolution
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nms_scatter_kernel(const int2 *__restrict__ edges, const NmsCounters *__restrict__ ctr,
+                   unsigned long long edge_cap, const int32_t *__restrict__ offs,
+                   int32_t *__restrict__ cursor, int32_t *__restrict__ adj)
+{
+    unsigned long long ne = ctr->edges < edge_cap ? ctr->edges : edge_cap;
+    for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < ne;
+         e += (unsigned long long)gridDim.x * blockDim.x) {
+        int2 ed = edges[e];
+        int pos = offs[ed.x] + atomicAdd(&cursor[ed.x], 1);
+        adj[pos] = ed.y;
+    }
+}
+
+// status by rank: 0 undecided, 1 kept, 2 suppressed
+__global__ void __launch_bounds__(256)
+nms_resolve_kernel(const int32_t *__restrict__ offs, const int32_t *__restrict__ adj, int n,
+                   volatile uint8_t *status, int *changed /* [2] */, NmsCounters *ctr)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nth = gridDim.x * blockDim.x;
+    int round = 0;
+    while (true) {
+        int *flag = &changed[round & 1];
+        int local = 0;
+        for (int r = tid; r < n; r += nth) {
+            if (status[r] != 0) continue;
+            const int b = offs[r], e = offs[r + 1];
+            bool any_keep = false, all_supp = true;
+            for (int k = b; k < e; ++k) {
+                const uint8_t s = status[adj[k]];
+                if (s == 1) { any_keep = true; break; }
+                if (s == 0) all_supp = false;
+            }
+            if (any_keep) { status[r] = 2; local = 1; }
+            else if (all_supp) { status[r] = 1; local = 1; }
+        }
+        if (local) *flag = 1;
+        __threadfence();
+        grid.sync();
+        const int any = *(volatile int *)flag;
+        if (tid == 0) changed[(round + 1) & 1] = 0;
+        ++round;
+        grid.sync();
+        if (!any) break;
+    }
+    if (tid == 0) ctr->rounds = round;
+}
+
+__global__ void __launch_bounds__(256)
+nms_flags_kernel(const uint8_t *__restrict__ status, const int32_t *__restrict__ order,
+                 const int32_t *__restrict__ rank, int n, int out_order,
+                 uint8_t *__restrict__ flags, int64_t *__restrict__ vals)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (out_order == ORP_ORDER_SCORE_DESC) {
+        flags[k] = status[k] == 1;
+        vals[k] = order[k];
+    } else {
+        flags[k] = status[rank[k]] == 1;
+        vals[k] = k;
+    }
+}
+
+static int run_nms(const float *dets, const int32_t *segments, int n, double thr, int iou_mode,
+                   int union_mode, int order, int64_t *keep_out, int32_t *num_out, cudaStream_t st)
+{
+    if (n < 0 || !num_out || (n > 0 && (!dets || !keep_out)))
+        return fail(ORP_EINVAL, "orp_rnms: null pointer or negative n");
+    if (iou_mode != ORP_NMS_EXACT64 && iou_mode != ORP_NMS_COMPAT32) return fail(ORP_EINVAL, "orp_rnms: bad iou_mode");
+    if (union_mode < 0 || union_mode > 2) return fail(ORP_EINVAL, "orp_rnms: bad union_mode");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (n == 0) {
+        ORP_CUDA(cudaMemsetAsync(num_out, 0, sizeof(int32_t), st));
+        return ORP_OK;
+    }
+    Scratch S(st);
+    const int T = 256, G = ceil_div(n, T);
+    uint32_t *score_key = S.get<uint32_t>(n), *score_key2 = S.get<uint32_t>(n);
+    uint64_t *sweep_key = S.get<uint64_t>(n), *sweep_key2 = S.get<uint64_t>(n);
+    int32_t *iota = S.get<int32_t>(n), *order_r = S.get<int32_t>(n), *perm = S.get<int32_t>(n);
+    int32_t *rank = S.get<int32_t>(n);
+    float4 *aabb = S.get<float4>(n), *v01 = S.get<float4>(n), *v23 = S.get<float4>(n);
+    int32_t *rk = S.get<int32_t>(n), *sg = S.get<int32_t>(n), *nvalid = S.get<int32_t>(1);
+    float *area = S.get<float>(n);
+    int32_t *indeg = S.get<int32_t>(n + 1), *offs = S.get<int32_t>(n + 1), *cursor = S.get<int32_t>(n + 1);
+    uint8_t *status = S.get<uint8_t>(n), *flags = S.get<uint8_t>(n);
+    int64_t *vals = S.get<int64_t>(n);
+    int *changed = S.get<int>(2);
+    NmsCounters *ctr = S.get<NmsCounters>(1);
+    if (!ctr || !vals || !changed) return fail(ORP_ECUDA, "orp_rnms: scratch allocation failed");
+
+    size_t tb1 = 0, tb2 = 0, tb3 = 0, tb4 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb1, score_key, score_key2, iota, order_r, n, 0, 32, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb2, sweep_key, sweep_key2, iota, perm, n, 0, 64, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb3, indeg, offs, n + 1, st);
+    cub::DeviceSelect::Flagged(nullptr, tb4, vals, flags, keep_out, num_out, n, st);
+    size_t tb = tb1 > tb2 ? tb1 : tb2;
+    tb = tb > tb3 ? tb : tb3;
+    tb = tb > tb4 ? tb : tb4;
+    uint8_t *tmp = S.get<uint8_t>(tb);
+    if (!tmp) return fail(ORP_ECUDA, "orp_rnms: scratch allocation failed");
+
+    ORP_CUDA(cudaMemsetAsync(ctr, 0, sizeof(NmsCounters), st));
+    ORP_CUDA(cudaMemsetAsync(indeg, 0, sizeof(int32_t) * (size_t)(n + 1), st));
+    ORP_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)(n + 1), st));
+    ORP_CUDA(cudaMemsetAsync(status, 0, (size_t)n, st));
+    ORP_CUDA(cudaMemsetAsync(changed, 0, 2 * sizeof(int), st));
+
+    nms_prep_kernel<<<G, T, 0, st>>>(dets, segments, n, score_key, sweep_key, iota);
+    ORP_LAUNCHED();
+    ORP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb1, score_key, score_key2, iota, order_r, n, 0, 32, st));
+    count_launches(4);
+    nms_rank_kernel<<<G, T, 0, st>>>(order_r, n, rank);
+    ORP_LAUNCHED();
+
+    // edge buffer: grows on overflow (one retry costs a host sync; sized to make that rare)
+    unsigned long long cap = (unsigned long long)n * 64ull;
+    if (cap < (1ull << 20)) cap = 1ull << 20;
+    const unsigned long long all_pairs = (unsigned long long)n * (unsigned long long)(n - 1) / 2ull;
+    if (cap > all_pairs) cap = all_pairs ? all_pairs : 1;
+
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        int2 *edges = S.get<int2>(cap);
+        if (!edges) return fail(ORP_ECUDA, "orp_rnms: edge buffer allocation failed");
+        if (iou_mode == ORP_NMS_EXACT64) {
+            if (attempt == 0) {
+                ORP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb2, sweep_key, sweep_key2, iota, perm, n, 0, 64, st));
+                count_launches(8);
+                nms_gather_kernel<<<G, T, 0, st>>>(dets, segments, perm, sweep_key2, rank, n, aabb, v01, v23,
+                                                   rk, sg, area, nvalid);
+                ORP_LAUNCHED();
+            }
+            SweepParams P{aabb, v01, v23, rk, sg, area, nvalid, edges, indeg, cap, ctr, thr, union_mode};
+            int grid = ceil_div(n, kSweepWarps);
+            const int maxgrid = 148 * 8 * 4;
+            if (grid > maxgrid) grid = maxgrid;
+            nms_sweep_kernel<<<grid, kSweepWarps * 32, 0, st>>>(P);
+            ORP_LAUNCHED();
+        } else {
+            if (attempt == 0) {
+                nms_gather_kernel<<<G, T, 0, st>>>(dets, segments, order_r, nullptr, rank, n, aabb, v01, v23, rk,
+                                                   sg, area, nvalid);
+                ORP_LAUNCHED();
+            }
+            const long long nb = (n + 63) / 64;
+            const long long tiles = nb * (nb + 1) / 2;
+            if (tiles > 2147483647LL) return fail(ORP_EINVAL, "orp_rnms: n too large for COMPAT32 mode");
+            nms_compat_tiles_kernel<<<(unsigned)tiles, 64, 0, st>>>(v01, v23, sg, n, (float)thr, union_mode, edges,
+                                                                    indeg, cap, ctr);
+            ORP_LAUNCHED();
+        }
+        if (cap >= all_pairs) break;   // cannot overflow
+        // overflow check needs the host; it is the only sync of the call and only happens when
+        // the edge list could in principle exceed its capacity
+        NmsCounters h;
+        ORP_CUDA(cudaMemcpyAsync(&h, ctr, sizeof(h), cudaMemcpyDeviceToHost, st));
+        ORP_CUDA(cudaStreamSynchronize(st));
+        if (!h.overflow) break;
+        if (attempt == 5) return fail(ORP_EOVERFLOW, "orp_rnms: edge buffer overflow");
+        cap = h.edges + h.edges / 8 + 1024;
+        if (cap > all_pairs) cap = all_pairs;
+        ORP_CUDA(cudaMemsetAsync(ctr, 0, sizeof(NmsCounters), st));
+        ORP_CUDA(cudaMemsetAsync(indeg, 0, sizeof(int32_t) * (size_t)(n + 1), st));
+    }
+    // the loop above leaves `edges` as the last buffer obtained from S
+    int2 *edges = static_cast<int2 *>(S.ptrs[S.n - 1]);
+
+    ORP_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb3, indeg, offs, n + 1, st));
+    count_launches(2);
+    int32_t *adj = S.get<int32_t>(cap);
+    if (!adj) return fail(ORP_ECUDA, "orp_rnms: adjacency allocation failed");
+    {
+        int grid = 148 * 8;
+        nms_scatter_kernel<<<grid, 256, 0, st>>>(edges, ctr, cap, offs, cursor, adj);
+        ORP_LAUNCHED();
+    }
+    {
+        int dev = 0, sms = 0, per_sm = 0;
+        ORP_CUDA(cudaGetDevice(&dev));
+        ORP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        ORP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_resolve_kernel, 256, 0));
+        if (per_sm > 4) per_sm = 4;
+        int grid = sms * (per_sm > 0 ? per_sm : 1);
+        int need = ceil_div(n, 256);
+        if (grid > need) grid = need;
+        const int32_t *a0 = offs, *a1 = adj;
+        int a2 = n;
+        volatile uint8_t *a3 = status;
+        int *a4 = changed;
+        NmsCounters *a5 = ctr;
+        void *args[] = {&a0, &a1, &a2, &a3, &a4, &a5};
+        ORP_CUDA(cudaLaunchCooperativeKernel((void *)nms_resolve_kernel, dim3(grid), dim3(256), args, 0, st));
+        ORP_LAUNCHED();
+    }
+    nms_flags_kernel<<<G, T, 0, st>>>(status, order_r, rank, n, order, flags, vals);
+    ORP_LAUNCHED();
+    ORP_CUDA(cub::DeviceSelect::Flagged(tmp, tb4, vals, flags, keep_out, num_out, n, st));
+    count_launches(3);
+
+    // stash the counters for orp_rnms_last_stats (async copy into pinned memory)
+    if (!g_stats_pinned) ORP_CUDA(cudaHostAlloc(&g_stats_pinned, sizeof(NmsCounters), cudaHostAllocDefault));
+    ORP_CUDA(cudaMemcpyAsync(g_stats_pinned, ctr, sizeof(NmsCounters), cudaMemcpyDeviceToHost, st));
+    g_last_stats.n = n;
+    return ORP_OK;
+}
+
+}  // namespace orp
+
+extern "C" int orp_rnms(const float *dets, const int32_t *segments, int n, double iou_thr, int iou_mode,
+                        int union_mode, int order, int64_t *keep_out, int32_t *num_out, void *stream)
+{
+    return orp::run_nms(dets, segments, n, iou_thr, iou_mode, union_mode, order, keep_out, num_out,
+                        static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int orp_rnms_last_stats(orp_nms_stats *out)
+{
+    if (!out) return orp::fail(ORP_EINVAL, "orp_rnms_last_stats: null");
+    if (!orp::g_stats_pinned) return orp::fail(ORP_EINVAL, "orp_rnms_last_stats: no previous call");
+    const orp::NmsCounters &c = *orp::g_stats_pinned;
+    out->pairs_total = (int64_t)c.pairs_swept;
+    out->pairs_aabb = (int64_t)c.pairs_aabb;
+    out->pairs_clipped = (int64_t)c.pairs_clipped;
+    out->pairs_fp64 = (int64_t)c.pairs_fp64;
+    out->edges = (int64_t)c.edges;
+    out->rounds = c.rounds;
+    out->n = orp::g_last_stats.n;
+    return ORP_OK;
+}
+
+extern "C" int orp_poly_nms_host(int *keep_out, int *num_out, const float *polys_host, int polys_num,
+                                 int polys_dim, float nms_overlap_thresh, int device_id)
+{
+    using namespace orp;
+    if (polys_dim != 9) return fail(ORP_EINVAL, "orp_poly_nms_host: polys_dim must be 9");
+    if (polys_num < 0 || !num_out || (polys_num > 0 && (!keep_out || !polys_host)))
+        return fail(ORP_EINVAL, "orp_poly_nms_host: bad arguments");
+    if (polys_num == 0) { *num_out = 0; return ORP_OK; }
+    int prev = 0;
+    ORP_CUDA(cudaGetDevice(&prev));
+    ORP_CUDA(cudaSetDevice(device_id));
+    cudaStream_t st;
+    ORP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int rc = ORP_OK;
+    float *d = nullptr;
+    int64_t *k = nullptr;
+    int32_t *cnt = nullptr;
+    do {
+        if (cudaMallocAsync(&d, sizeof(float) * 9 * (size_t)polys_num, st) != cudaSuccess ||
+            cudaMallocAsync(&k, sizeof(int64_t) * (size_t)polys_num, st) != cudaSuccess ||
+            cudaMallocAsync(&cnt, sizeof(int32_t), st) != cudaSuccess) { rc = fail(ORP_ECUDA, "orp_poly_nms_host: alloc"); break; }
+        if (cudaMemcpyAsync(d, polys_host, sizeof(float) * 9 * (size_t)polys_num, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = fail(ORP_ECUDA, "orp_poly_nms_host: h2d"); break; }
+        // the caller sorted by score already (poly_nms.pyx:19-21); our stable descending sort
+        // reproduces that order exactly, so SCORE_DESC output == positions in the sorted input
+        rc = run_nms(d, nullptr, polys_num, (double)nms_overlap_thresh, ORP_NMS_EXACT64, ORP_UNION_GUARD,
+                     ORP_ORDER_SCORE_DESC, k, cnt, st);
+        if (rc) break;
+        int32_t hc = 0;
+        if (cudaMemcpyAsync(&hc, cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { rc = fail(ORP_ECUDA, "orp_poly_nms_host: d2h"); break; }
+        int64_t *hk = (int64_t *)malloc(sizeof(int64_t) * (size_t)(hc > 0 ? hc : 1));
+        if (cudaMemcpy(hk, k, sizeof(int64_t) * (size_t)hc, cudaMemcpyDeviceToHost) != cudaSuccess) { free(hk); rc = fail(ORP_ECUDA, "orp_poly_nms_host: d2h keep"); break; }
+        for (int i = 0; i < hc; ++i) keep_out[i] = (int)hk[i];
+        free(hk);
+        *num_out = hc;
+    } while (0);
+    if (d) cudaFreeAsync(d, st);
+    if (k) cudaFreeAsync(k, st);
+    if (cnt) cudaFreeAsync(cnt, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    cudaSetDevice(prev);
+    return rc;
+}

@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py - measurement harness of the OrientedRepPoints B200 hot path (contract in the task brief).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                 # our arm, one JSON line
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 # reference CPU arm, one JSON line
+    torchrun ... bench.py --gpus N ...                             # one rank per GPU (weak scaling)
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+  workload r50_tile (default once the dense path is built): one 1024x1024 tile through R-50 + FPN +
+      OrientedRepPointsHead + minaerarect + multiclass_rnms (BASELINE.json configs[1]); metric tiles/s.
+  workload nms_100k: rotated NMS (thr 0.1) over 100k synthetic proposals in a 1024^2 extent
+      (BASELINE.json configs[2] at its 100k point); metric Mpairs/s with pairs = N(N-1)/2.
+Timing: CUDA events on the launching stream around every step, an L2 flush (write of a 512 MiB buffer)
+between timed steps, barrier + synchronize on both sides of the timed region, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, help="r50_tile | nms_100k | nms_100k_sparse")
+    ap.add_argument("--boxes", type=int, default=100000)
+    ap.add_argument("--batch", type=int, default=None, help="tiles per step per GPU (r50_tile)")
+    ap.add_argument("--precision", default=None, help="r50_tile arithmetic: bf16 | fp32")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def dist_setup(n_gpus):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+def barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    import torch
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                    "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------------- NMS workload
+def nms_algorithmic_bytes(n):
+    """boxes 36 N + bit-mask write and read 16 N ceil(N/64)  (~0.5 B per pair)."""
+    return 36.0 * n + 16.0 * n * ((n + 63) // 64)
+
+
+def run_nms(args, rank, world, local, dense=True):
+    import torch
+    from oracle import pyoracle as po   # input generator only (shared with the tests)
+    from orientedreppoints_b200 import _lib
+    from orientedreppoints_b200.dota.poly_nms_gpu import poly_gpu_nms
+    from orientedreppoints_b200.ops import rnms_indices
+    n = args.boxes
+    extent = 1024.0 if dense else 1024.0 * np.sqrt(n / 1000.0)
+    dets_h = po.gen_rotated_boxes(n, seed=100 + rank, extent=extent)       # per-rank shard, fixed size: weak scaling
+    dev = torch.device("cuda", local)
+    dets = torch.from_numpy(dets_h).to(dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    thr = 0.1
+    _lib.set_timing(True)
+
+    def step():
+        return rnms_indices(dets, thr, order=_lib.ORP_ORDER_SCORE_DESC, return_count_tensor=True)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier(world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sweep_ms = []
+    barrier(world)
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)                                              # L2 flush, not timed
+        ev[s][0].record()
+        keep, cnt = step()
+        ev[s][1].record()
+        sweep_ms.append(None)
+        torch.cuda.current_stream().synchronize()
+        sweep_ms[-1] = _lib.last_sweep_ms()
+    barrier(world)
+    launches = _lib.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    total_ms = max_over_ranks(total_ms, world)
+    kept = int(cnt.item())
+    stats = _lib.last_nms_stats()
+    pairs = n * (n - 1) / 2.0
+
+    # end to end through the reference-facing host API (numpy in, python list out)
+    for _ in range(2):
+        poly_gpu_nms(dets_h, thr, device_id=local)
+    barrier(world)
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        kl = poly_gpu_nms(dets_h, thr, device_id=local)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_ms = max_over_ranks(e2e_ms, world)
+    assert len(kl) == kept
+
+    pk = peaks()
+    sweep_avg = float(np.mean(sweep_ms))
+    ach = nms_algorithmic_bytes(n) / (sweep_avg * 1e-3) / 1e9
+    line = {
+        "metric": "rotated IoU+NMS Mpairs/sec", "value": world * pairs / (total_ms / args.steps * 1e-3) / 1e6,
+        "unit": "Mpairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (+f64 inside the decision band)", "data": "synthetic",
+        "config": {"workload": "poly_nms %d rotated proposals in %s, IoU thr 0.1, one set per GPU" %
+                   (n, "a 1024x1024 extent (dense)" if dense else "constant 1k/1024^2 density"),
+                   "l2": "512 MiB flush write between timed steps", "kept": kept,
+                   "pairs_swept": stats["pairs_total"], "pairs_aabb": stats["pairs_aabb"],
+                   "pairs_clipped": stats["pairs_clipped"], "pairs_fp64": stats["pairs_fp64"],
+                   "edges": stats["edges"], "rounds": stats["rounds"],
+                   "prefilter_hit_rate": stats["pairs_aabb"] / pairs},
+        "gpu_launches": int(launches),
+        "e2e": {"value": world * pairs / (e2e_ms * 1e-3) / 1e6, "unit": "Mpairs/s",
+                "h2d_bytes_per_step": int(dets_h.nbytes), "d2h_bytes_per_step": int(kept * 8 + 4),
+                "api": "DOTA_devkit.poly_nms_gpu.poly_gpu_nms(np.float32[N,9], thr) -> list"},
+        "roofline": {"bound": "hbm", "kernel": "nms_sweep_kernel", "achieved": ach, "peak": pk["hbm_gbs"],
+                     "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                     "algorithmic_bytes_per_launch": nms_algorithmic_bytes(n), "kernel_ms": sweep_avg,
+                     "kernel_share_of_step": sweep_avg / (total_ms / args.steps)},
+    }
+    if clocks is not None:
+        line["clocks"] = clocks
+    return line
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def cpu_baseline_block(n_boxes, shards):
+    from oracle import ref_driver
+    b = ref_driver.timed_baseline(n_boxes, 0.1, shards)
+    return {"value": b["value"], "unit": "Mpairs/s", "cores": b["cores"], "kind": b["kind"], "sample": b["sample"],
+            "seconds": b["seconds"]}
+
+
+def run_reference(args, rank, world):
+    """the reference's own CPU implementation of the geometry path on the host cores"""
+    if rank != 0:
+        return None
+    cores = os.cpu_count() or 1
+    shards = max(1, min(cores, 16))
+    vals, secs = [], []
+    nb = 1500
+    for _ in range(args.warmup):
+        cpu_baseline_block(300, shards)
+    last = None
+    for _ in range(args.steps):
+        last = cpu_baseline_block(nb, shards)
+        vals.append(last["value"])
+        secs.append(last["seconds"])
+    v = float(np.mean(vals))
+    return {"impl": "reference", "metric": "rotated IoU+NMS Mpairs/sec", "value": v, "unit": "Mpairs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "bounded sample of the poly_nms workload: " + last["sample"]},
+            "cpu_baseline": {"value": v, "unit": "Mpairs/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+            "e2e": {"value": v, "unit": "Mpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        line = run_reference(args, rank, world)
+        if line is not None:
+            print(json.dumps(line))
+        return 0
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "bench.py needs a GPU: the product path has no CPU fallback"}))
+        return 1
+    rank, world, local = dist_setup(args.gpus)
+    workload = args.workload
+    if workload is None:
+        try:
+            from orientedreppoints_b200 import bench_tile  # noqa: F401  (dense path present?)
+            workload = "r50_tile"
+        except ImportError:
+            workload = "nms_100k"
+    if workload == "r50_tile":
+        from orientedreppoints_b200 import bench_tile
+        line = bench_tile.run(args, rank, world, local, sys.modules[__name__])
+    elif workload in ("nms_100k", "nms_100k_sparse"):
+        line = run_nms(args, rank, world, local, dense=(workload == "nms_100k"))
+    else:
+        raise SystemExit("unknown workload " + workload)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        line["cpu_baseline"] = cpu_baseline_block(2000, 1)
+        line["cpu_baseline"]["host_cores_available"] = cores
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

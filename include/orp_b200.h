@@ -109,6 +109,12 @@ typedef struct {
 } orp_nms_stats;
 int orp_rnms_last_stats(orp_nms_stats *out);
 
+/* Measurement hooks: with timing on, orp_rnms brackets its dominant kernel (the sweep+clip
+ * kernel) with CUDA events ON THE LAUNCHING STREAM; orp_rnms_last_sweep_ms waits for them and
+ * returns the elapsed device time of that kernel for the last call of this thread. */
+void orp_set_timing(int on);
+int orp_rnms_last_sweep_ms(float *ms);
+
 /* ------------------------------------------------------------------------------------------
  * Pairwise rotated IoU
  * ---------------------------------------------------------------------------------------- */

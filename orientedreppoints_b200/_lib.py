@@ -38,6 +38,8 @@ SIGNATURES = {
     "orp_rnms": (_i, [_vp, _vp, _i, _d, _i, _i, _i, _vp, _vp, _vp]),
     "orp_poly_nms_host": (_i, [_vp, _vp, _vp, _i, _i, _f, _i]),
     "orp_rnms_last_stats": (_i, [ctypes.POINTER(NmsStats)]),
+    "orp_set_timing": (None, [_i]),
+    "orp_rnms_last_sweep_ms": (_i, [ctypes.POINTER(ctypes.c_float)]),
     "orp_poly_overlaps_host": (_i, [_vp, _vp, _vp, _i, _i, _i]),
     "orp_poly_overlaps": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "orp_quad_iou_matrix": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),
@@ -88,6 +90,16 @@ def last_nms_stats():
     s = NmsStats()
     check(lib().orp_rnms_last_stats(ctypes.byref(s)), "orp_rnms_last_stats")
     return s.as_dict()
+
+
+def set_timing(on):
+    lib().orp_set_timing(1 if on else 0)
+
+
+def last_sweep_ms():
+    v = ctypes.c_float(0)
+    check(lib().orp_rnms_last_sweep_ms(ctypes.byref(v)), "orp_rnms_last_sweep_ms")
+    return float(v.value)
 
 
 def current_stream_ptr():

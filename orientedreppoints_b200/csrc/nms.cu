@@ -33,6 +33,8 @@ struct NmsCounters {
 };
 
 static thread_local orp_nms_stats g_last_stats;
+static int g_timing = 0;                                   // orp_set_timing()
+static thread_local cudaEvent_t g_ev[2] = {nullptr, nullptr};
 static thread_local NmsCounters *g_stats_dev = nullptr;   // device copy of the last call
 static thread_local NmsCounters *g_stats_pinned = nullptr;
 
@@ -487,7 +489,7 @@ static int run_nms(const float *dets, const int32_t *segments, int n, double thr
     ORP_LAUNCHED();
 
     // edge buffer: grows on overflow (one retry costs a host sync; sized to make that rare)
-    unsigned long long cap = (unsigned long long)n * 64ull;
+    unsigned long long cap = (unsigned long long)n * 256ull;
     if (cap < (1ull << 20)) cap = 1ull << 20;
     const unsigned long long all_pairs = (unsigned long long)n * (unsigned long long)(n - 1) / 2ull;
     if (cap > all_pairs) cap = all_pairs ? all_pairs : 1;
@@ -507,8 +509,13 @@ static int run_nms(const float *dets, const int32_t *segments, int n, double thr
             int grid = ceil_div(n, kSweepWarps);
             const int maxgrid = 148 * 8 * 4;
             if (grid > maxgrid) grid = maxgrid;
+            if (g_timing) {
+                if (!g_ev[0]) { ORP_CUDA(cudaEventCreate(&g_ev[0])); ORP_CUDA(cudaEventCreate(&g_ev[1])); }
+                ORP_CUDA(cudaEventRecord(g_ev[0], st));
+            }
             nms_sweep_kernel<<<grid, kSweepWarps * 32, 0, st>>>(P);
             ORP_LAUNCHED();
+            if (g_timing) ORP_CUDA(cudaEventRecord(g_ev[1], st));
         } else {
             if (attempt == 0) {
                 nms_gather_kernel<<<G, T, 0, st>>>(dets, segments, order_r, nullptr, rank, n, aabb, v01, v23, rk,
@@ -584,6 +591,17 @@ extern "C" int orp_rnms(const float *dets, const int32_t *segments, int n, doubl
 {
     return orp::run_nms(dets, segments, n, iou_thr, iou_mode, union_mode, order, keep_out, num_out,
                         static_cast<cudaStream_t>(stream));
+}
+
+extern "C" void orp_set_timing(int on) { orp::g_timing = on; }
+
+extern "C" int orp_rnms_last_sweep_ms(float *ms)
+{
+    if (!ms) return orp::fail(ORP_EINVAL, "orp_rnms_last_sweep_ms: null");
+    if (!orp::g_timing || !orp::g_ev[0]) return orp::fail(ORP_EINVAL, "orp_rnms_last_sweep_ms: timing is off");
+    ORP_CUDA(cudaEventSynchronize(orp::g_ev[1]));
+    ORP_CUDA(cudaEventElapsedTime(ms, orp::g_ev[0], orp::g_ev[1]));
+    return ORP_OK;
 }
 
 extern "C" int orp_rnms_last_stats(orp_nms_stats *out)

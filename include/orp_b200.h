@@ -163,6 +163,40 @@ int orp_box_iou_rotated(const float *boxes1, int n, const float *boxes2, int m, 
 int orp_minarearect(const float *pts, int n, float *out, int32_t *hull_map, float scale,
                     const float *center, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Dense layers, fp32 (CUDA cores) - the parity arithmetic of the backbone / FPN / head
+ * All activations are NHWC ("channels last") contiguous device tensors; weights are
+ * [Cout][KH][KW][Cin] (the reference's [Cout][Cin][KH][KW] permuted once at load time).
+ * ---------------------------------------------------------------------------------------- */
+
+/* y = relu?( conv(x, w) + bias + residual ), optionally accumulating the GroupNorm statistics of y:
+ * gn_stats is device double [N, groups, 2] (sum, sum of squares), must be zeroed by the caller.
+ * Replaces nn.Conv2d / ConvModule.conv (mmdet/ops/conv_module.py:124-132) on the cuDNN path; with
+ * eval-mode BatchNorm folded into w and bias beforehand (the fold of tools/fuse_conv_bn.py:10-24). */
+int orp_conv2d_f32(const float *x, int N, int H, int W, int Cin, const float *w, int Cout, int KH, int KW,
+                   int stride, int pad, const float *bias, const float *residual, int relu, float *y,
+                   double *gn_stats, int groups, void *stream);
+
+/* Deformable convolution forward (DCNv1; DCNv2 when mask != NULL), deformable_groups = groups = 1.
+ * Replaces deform_conv_forward_cuda / modulated_deform_conv_cuda_forward
+ * (mmdet/ops/dcn/src/deform_conv_cuda.cpp:152-260, 490-569) without the im2col `columns` scratch:
+ * sampling per deformable_im2col_bilinear (deform_conv_cuda_kernel.cu:84-115), validity test of :229.
+ *   offset  device float32 [N, Ho, Wo, 2*KH*KW], channel 2t = dy, 2t+1 = dx of tap t (:222-225)
+ *   mask    device float32 [N, Ho, Wo, KH*KW] or NULL */
+int orp_deform_conv2d_f32(const float *x, int N, int H, int W, int Cin, const float *offset, const float *mask,
+                          const float *w, int Cout, int KH, int KW, int stride, int pad, int dilation,
+                          const float *bias, int relu, float *y, void *stream);
+
+/* GroupNorm apply: y = relu?( (x - mean) * rstd * gamma + beta ) (+ nearest-2x upsampled up_src,
+ * the FPN top-down add of mmdet/models/necks/fpn.py:150-154).  stats as produced by orp_conv2d_f32;
+ * biased variance and eps as torch.nn.GroupNorm (mmdet/ops/norm.py:42-50). */
+int orp_gn_apply_f32(const float *x, int N, int H, int W, int C, const double *stats, int groups,
+                     const float *gamma, const float *beta, float eps, int relu, const float *up_src, float *y,
+                     void *stream);
+
+/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of the ResNet stem (resnet.py:497) */
+int orp_maxpool3x3s2_f32(const float *x, int N, int H, int W, int C, float *y, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,216 @@
+"""OrientedRepPointsDetector inference (simple_test path) over liborp_b200.so.
+
+Mirrors mmdet/models/detectors/orientedreppoints_detector.py:37-46:
+    x = extract_feat(img)            # single_stage.py:44-50: backbone -> neck
+    outs = bbox_head(x)              # orientedreppoints_head.py:173: forward_single per level
+    bbox_list = bbox_head.get_bboxes(*outs, img_meta, test_cfg, rescale)
+    rbbox2result(...)                # core/bbox/transforms.py:356-375
+
+Host code is Python; every layer is a kernel of this repository called through the C ABI
+(include/orp_b200.h) on torch-owned device memory and the current torch stream.  Activations are NHWC.
+Two arithmetic engines: 'fp32' (CUDA-core FMAs - the parity arithmetic) and 'bf16' (tcgen05 tensor
+cores, fp32 accumulation in TMEM).  There is no PyTorch/cuDNN fallback for any layer.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .weights import STAGE_BLOCKS, fold_bn
+
+STRIDES = (8, 16, 32, 64, 128)
+
+
+class ConvLayer:
+    """weights of one convolution in kernel layout [Cout, KH, KW, Cin] (+ optional bias)"""
+
+    def __init__(self, w_nchw, bias, stride, pad, device, pad_cin_to=None):
+        w = w_nchw.permute(0, 2, 3, 1).contiguous()                   # [Cout, KH, KW, Cin]
+        if pad_cin_to is not None and w.shape[3] < pad_cin_to:
+            w = torch.cat([w, w.new_zeros(*w.shape[:3], pad_cin_to - w.shape[3])], 3).contiguous()
+        self.cout, self.kh, self.kw, self.cin = w.shape
+        self.w = w.to(device=device, dtype=torch.float32).contiguous()
+        self.bias = None if bias is None else bias.to(device=device, dtype=torch.float32).contiguous()
+        self.stride, self.pad = stride, pad
+        self.tc = None    # tensor-core operand cache (dense_tc), filled lazily by the bf16 engine
+
+
+class Norm:
+    def __init__(self, sd, prefix, device):
+        self.gamma = sd[prefix + ".weight"].to(device=device, dtype=torch.float32).contiguous()
+        self.beta = sd[prefix + ".bias"].to(device=device, dtype=torch.float32).contiguous()
+
+
+class EngineF32:
+    """fp32 CUDA-core kernels (csrc/dense_f32.cu)"""
+    name = "fp32"
+    act_dtype = torch.float32
+
+    def __init__(self, device):
+        self.device = device
+        self.lib = _lib.lib()
+
+    def prepare_input(self, img_nchw):
+        n, c, h, w = img_nchw.shape
+        x = torch.zeros((n, h, w, 4), dtype=torch.float32, device=self.device)
+        x[..., :c] = img_nchw.to(self.device, torch.float32).permute(0, 2, 3, 1)
+        return x
+
+    def conv(self, x, L, relu=False, residual=None, want_stats=False):
+        n, h, w, cin = x.shape
+        assert cin == L.cin, (cin, L.cin)
+        ho = (h + 2 * L.pad - L.kh) // L.stride + 1
+        wo = (w + 2 * L.pad - L.kw) // L.stride + 1
+        y = torch.empty((n, ho, wo, L.cout), dtype=torch.float32, device=self.device)
+        stats = torch.zeros((n, 32, 2), dtype=torch.float64, device=self.device) if want_stats else None
+        rc = self.lib.orp_conv2d_f32(_lib.ptr(x), n, h, w, cin, _lib.ptr(L.w), L.cout, L.kh, L.kw, L.stride, L.pad,
+                                     _lib.ptr(L.bias), _lib.ptr(residual), int(relu), _lib.ptr(y), _lib.ptr(stats), 32,
+                                     _lib.current_stream_ptr())
+        _lib.check(rc, "orp_conv2d_f32")
+        return (y, stats) if want_stats else y
+
+    def gn(self, x, stats, norm, relu=False, up=None):
+        n, h, w, c = x.shape
+        y = torch.empty_like(x)
+        rc = self.lib.orp_gn_apply_f32(_lib.ptr(x), n, h, w, c, _lib.ptr(stats), 32, _lib.ptr(norm.gamma),
+                                       _lib.ptr(norm.beta), 1e-5, int(relu), _lib.ptr(up), _lib.ptr(y),
+                                       _lib.current_stream_ptr())
+        _lib.check(rc, "orp_gn_apply_f32")
+        return y
+
+    def conv_gn(self, x, L, norm, relu=False, up=None):
+        y, st = self.conv(x, L, want_stats=True)
+        return self.gn(y, st, norm, relu=relu, up=up)
+
+    def maxpool(self, x):
+        n, h, w, c = x.shape
+        ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+        y = torch.empty((n, ho, wo, c), dtype=torch.float32, device=self.device)
+        rc = self.lib.orp_maxpool3x3s2_f32(_lib.ptr(x), n, h, w, c, _lib.ptr(y), _lib.current_stream_ptr())
+        _lib.check(rc, "orp_maxpool3x3s2_f32")
+        return y
+
+    def deform_conv(self, x, offset, L, relu=False, mask=None):
+        n, h, w, cin = x.shape
+        y = torch.empty((n, h, w, L.cout), dtype=torch.float32, device=self.device)
+        rc = self.lib.orp_deform_conv2d_f32(_lib.ptr(x), n, h, w, cin, _lib.ptr(offset), _lib.ptr(mask), _lib.ptr(L.w),
+                                            L.cout, L.kh, L.kw, L.stride, L.pad, 1, _lib.ptr(L.bias), int(relu),
+                                            _lib.ptr(y), _lib.current_stream_ptr())
+        _lib.check(rc, "orp_deform_conv2d_f32")
+        return y
+
+    def to_f32(self, x):
+        return x
+
+
+class OrientedRepPointsDetector:
+    """R-50 / R-101 + FPN(GN) + OrientedRepPointsHead, inference only."""
+
+    def __init__(self, state_dict, depth=50, device="cuda", precision="fp32", test_cfg=None):
+        self.device = torch.device(device)
+        self.depth = depth
+        self.test_cfg = dict(nms_pre=2000, min_bbox_size=0, score_thr=0.05, nms=dict(type='rnms', iou_thr=0.4),
+                             max_per_img=2000)                         # configs/dota/orientedrepoints_r50_demo.py:62-67
+        if test_cfg:
+            self.test_cfg.update(test_cfg)
+        if precision == "fp32":
+            self.eng = EngineF32(self.device)
+        elif precision == "bf16":
+            from .engine_tc import EngineTC
+            self.eng = EngineTC(self.device)
+        else:
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self._load(state_dict)
+        base = np.arange(-1, 2).astype(np.float64)
+        off = np.stack([np.repeat(base, 3), np.tile(base, 3)], axis=1).reshape(-1)        # head :78-88 (dy,dx)
+        self.dcn_base_offset = torch.tensor(off, dtype=torch.float32, device=self.device).view(1, 1, 1, 18)
+
+    # ------------------------------------------------------------------ weights
+    def _load(self, sd):
+        d = self.device
+
+        def folded(conv, bn, stride, pad, pad_cin_to=None):
+            w, b = fold_bn(sd[conv + ".weight"].float(), sd[bn + ".weight"].float(), sd[bn + ".bias"].float(),
+                           sd[bn + ".running_mean"].float(), sd[bn + ".running_var"].float())
+            return ConvLayer(w, b, stride, pad, d, pad_cin_to)
+
+        self.stem = folded("backbone.conv1", "backbone.bn1", 2, 3, pad_cin_to=4)
+        self.blocks = []
+        for li, nblk in enumerate(STAGE_BLOCKS[self.depth]):
+            stage = []
+            for b in range(nblk):
+                p = "backbone.layer%d.%d" % (li + 1, b)
+                s = 2 if (b == 0 and li > 0) else 1
+                blk = dict(c1=folded(p + ".conv1", p + ".bn1", 1, 0), c2=folded(p + ".conv2", p + ".bn2", s, 1),
+                           c3=folded(p + ".conv3", p + ".bn3", 1, 0),
+                           ds=folded(p + ".downsample.0", p + ".downsample.1", s, 0) if b == 0 else None)
+                stage.append(blk)
+            self.blocks.append(stage)
+        self.lat = [(ConvLayer(sd["neck.lateral_convs.%d.conv.weight" % i].float(), None, 1, 0, d),
+                     Norm(sd, "neck.lateral_convs.%d.gn" % i, d)) for i in range(3)]
+        self.fpn = [(ConvLayer(sd["neck.fpn_convs.%d.conv.weight" % i].float(), None, 2 if i >= 3 else 1, 1, d),
+                     Norm(sd, "neck.fpn_convs.%d.gn" % i, d)) for i in range(5)]
+        h = "bbox_head."
+        self.cls_convs = [(ConvLayer(sd[h + "cls_convs.%d.conv.weight" % i].float(), None, 1, 1, d),
+                           Norm(sd, h + "cls_convs.%d.gn" % i, d)) for i in range(3)]
+        self.reg_convs = [(ConvLayer(sd[h + "reg_convs.%d.conv.weight" % i].float(), None, 1, 1, d),
+                           Norm(sd, h + "reg_convs.%d.gn" % i, d)) for i in range(3)]
+        r = h + "reppoints_"
+        self.cls_dcn = ConvLayer(sd[r + "cls_conv.weight"].float(), None, 1, 1, d)
+        self.cls_out = ConvLayer(sd[r + "cls_out.weight"].float(), sd[r + "cls_out.bias"].float(), 1, 0, d)
+        self.init_conv = ConvLayer(sd[r + "pts_init_conv.weight"].float(), sd[r + "pts_init_conv.bias"].float(), 1, 1, d)
+        self.init_out = ConvLayer(sd[r + "pts_init_out.weight"].float(), sd[r + "pts_init_out.bias"].float(), 1, 0, d)
+        self.ref_dcn = ConvLayer(sd[r + "pts_refine_conv.weight"].float(), None, 1, 1, d)
+        self.ref_out = ConvLayer(sd[r + "pts_refine_out.weight"].float(), sd[r + "pts_refine_out.bias"].float(), 1, 0, d)
+
+    # ------------------------------------------------------------------ dense graph
+    def extract_feat(self, img):
+        e = self.eng
+        x = e.prepare_input(img)
+        x = e.maxpool(e.conv(x, self.stem, relu=True))
+        feats = []
+        for stage in self.blocks:
+            for blk in stage:
+                idt = x if blk["ds"] is None else e.conv(x, blk["ds"])
+                o = e.conv(x, blk["c1"], relu=True)
+                o = e.conv(o, blk["c2"], relu=True)
+                x = e.conv(o, blk["c3"], relu=True, residual=idt)
+            feats.append(x)
+        c3, c4, c5 = feats[1], feats[2], feats[3]
+        l2 = e.conv_gn(c5, *self.lat[2])
+        l1 = e.conv_gn(c4, *self.lat[1], up=l2)
+        l0 = e.conv_gn(c3, *self.lat[0], up=l1)
+        outs = [e.conv_gn(l0, *self.fpn[0]), e.conv_gn(l1, *self.fpn[1]), e.conv_gn(l2, *self.fpn[2])]
+        outs.append(e.conv_gn(c5, *self.fpn[3]))
+        outs.append(e.conv_gn(outs[-1], *self.fpn[4]))
+        return outs
+
+    def head_single(self, x, gradient_mul=0.3):
+        e = self.eng
+        cf, pf = x, x
+        for (lc, nc), (lr, nr) in zip(self.cls_convs, self.reg_convs):
+            cf = e.conv_gn(cf, lc, nc, relu=True)
+            pf = e.conv_gn(pf, lr, nr, relu=True)
+        init = e.to_f32(e.conv(e.conv(pf, self.init_conv, relu=True), self.init_out))       # [N,H,W,18] fp32
+        # head :162-163, evaluated in fp32 exactly as written there
+        offset = ((1 - gradient_mul) * init + gradient_mul * init) - self.dcn_base_offset
+        offset = offset.contiguous()
+        cls = e.conv(e.deform_conv(cf, offset, self.cls_dcn, relu=True), self.cls_out)
+        ref = e.conv(e.deform_conv(pf, offset, self.ref_dcn, relu=True), self.ref_out, residual=init)
+        return e.to_f32(cls), init, e.to_f32(ref)
+
+    def forward_dense(self, img):
+        feats = self.extract_feat(img)
+        return [self.head_single(f) for f in feats], feats
+
+    # ------------------------------------------------------------------ simple_test
+    def simple_test(self, img, img_metas=None, rescale=True, return_tensors=False):
+        from .core.get_bboxes import get_bboxes
+        outs, _ = self.forward_dense(img)
+        n = img.shape[0]
+        if img_metas is None:
+            img_metas = [dict(scale_factor=1.0) for _ in range(n)]
+        results = get_bboxes([o[0] for o in outs], [o[2] for o in outs], STRIDES, img_metas, self.test_cfg, rescale)
+        if return_tensors:
+            return results
+        from .core.transforms import rbbox2result
+        return [rbbox2result(d, l, 16) for d, l in results]

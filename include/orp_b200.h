@@ -197,6 +197,40 @@ int orp_gn_apply_f32(const float *x, int N, int H, int W, int C, const double *s
 /* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of the ResNet stem (resnet.py:497) */
 int orp_maxpool3x3s2_f32(const float *x, int N, int H, int W, int C, float *y, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Dense layers, bf16 on the 5th-generation tensor cores (tcgen05.mma, fp32 accumulation in TMEM,
+ * operands staged by TMA).  Activations NHWC bf16; weights bf16 [Cout_padded][KH*KW*Cin] (K index =
+ * (kh*KW + kw)*Cin + ci; rows >= Cout are zero; Cout_padded a multiple of 32).
+ * ---------------------------------------------------------------------------------------- */
+
+/* one activation tensor of a multi-problem launch (e.g. one FPN level: the head's weights are shared
+ * by all five levels - orientedreppoints_head.py:173-174 multi_apply - so they run as ONE launch) */
+typedef struct {
+    const void *x;              /* bf16 NHWC [N,H,W,Cin]                                              */
+    int N, H, W;
+    void *out;                  /* bf16 (or fp32 when out_f32) NHWC [N,Ho,Wo,Cout]                    */
+    const void *residual_bf16;  /* optional bf16 NHWC [N,Ho,Wo,Cout], added before ReLU               */
+    const float *residual_f32;  /* optional fp32 NHWC [N,Ho,Wo,Cout] (head: refine += init, :168)     */
+    const float *offset;        /* deformable only: fp32 [N,Ho,Wo,2*KH*KW], (dy,dx) per tap           */
+} orp_tc_problem;
+
+/* y = relu?(conv(x, w) + bias + residual) for up to 5 problems sharing the weights.  deform != 0:
+ * the A operand is the bilinear sample of deform_conv_cuda_kernel.cu:84-115 (DCNv1, groups =
+ * deformable_groups = 1) produced on the fly in shared memory - no `columns` buffer. */
+int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const void *w, int Cout, int Cout_padded,
+                    int KH, int KW, int Cin, int stride, int pad, const float *bias, int relu, int out_f32,
+                    int deform, void *stream);
+
+/* conv1 of the ResNet stem as a GEMM: NCHW fp32 image -> bf16 [N,Ho,Wo,192] rows
+ * (k = (kh*7+kw)*3 + c, zero above 147) */
+int orp_stem_im2col_bf16(const float *img_nchw, int N, int H, int W, void *out, void *stream);
+int orp_maxpool3x3s2_bf16(const void *x, int N, int H, int W, int C, void *y, void *stream);
+/* GroupNorm over bf16 NHWC with C = 256, 32 groups: statistics (double [N,32,2], zeroed by caller) + apply */
+int orp_gn_stats_bf16(const void *x, int N, int HW, int C, int groups, double *stats, void *stream);
+int orp_gn_apply_bf16(const void *x, int N, int H, int W, int C, const double *stats, int groups,
+                      const float *gamma, const float *beta, float eps, int relu, const void *up_src, void *y,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,11 @@ class NmsStats(ctypes.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
+class TcProblem(ctypes.Structure):
+    _fields_ = [("x", _vp), ("N", _i), ("H", _i), ("W", _i), ("out", _vp), ("residual_bf16", _vp),
+                ("residual_f32", _vp), ("offset", _vp)]
+
+
 # name -> (restype, argtypes); every symbol include/orp_b200.h declares
 SIGNATURES = {
     "orp_last_error": (ctypes.c_char_p, []),
@@ -50,6 +55,11 @@ SIGNATURES = {
     "orp_deform_conv2d_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "orp_gn_apply_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _f, _i, _vp, _vp, _vp]),
     "orp_maxpool3x3s2_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "orp_conv2d_bf16": (_i, [_i, ctypes.POINTER(TcProblem), _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    "orp_stem_im2col_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "orp_maxpool3x3s2_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "orp_gn_stats_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "orp_gn_apply_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _f, _i, _vp, _vp, _vp]),
 }
 
 _LIB = None

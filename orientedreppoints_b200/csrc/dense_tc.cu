@@ -1,0 +1,555 @@
+// dense_tc.cu - tensor-core (tcgen05 / TMEM / TMA) implicit-GEMM convolution for sm_100a, NHWC bf16.
+//
+// Replaces the cuDNN convolutions of the reference's backbone / FPN / head towers
+// (mmdet/models/backbones/resnet.py:203-239,495-506; necks/fpn.py:138-178;
+// anchor_heads/orientedreppoints_head.py:153-168) and, in its gathered-operand variant, the deformable
+// im2col + SGEMM of mmdet/ops/dcn/src/deform_conv_cuda.cpp:152-260.
+//
+// GEMM view: D[M = 128 output pixels, N = BN output channels] += A[M, K] * B[N, K]^T with
+// K = taps x Cin walked in 64-channel blocks.  One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer: the A tile of one (tap, channel block) is ONE 4-D box {64 ch, BW, BH, BI}
+//               of the NHWC activation (tensor-map element strides = conv stride; out-of-bounds
+//               coordinates are zero-filled by the TMA unit = the convolution's zero padding), landing in
+//               shared memory as 128 rows x 128 B with the 128-byte swizzle - exactly the canonical
+//               K-major operand layout of tcgen05.mma; the B tile is a 2-D box of the [Cout, K] weights.
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN,
+//               K=16) x 4 per stage, accumulating fp32 in TMEM; tcgen05.commit releases the stage and,
+//               after the last K block, publishes the accumulator.
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns), bias / residual / ReLU, bf16 or fp32 NHWC
+//               stores.  TMEM holds two accumulators so the epilogue of tile i overlaps the main loop
+//               of tile i+1.
+//   warps 6-9   (deformable variant only) A-operand producers: per output pixel and tap the 4-corner
+//               bilinear sample of the reference (deform_conv_cuda_kernel.cu:84-115) is computed in
+//               fp32 from bf16 features and written to shared memory in the same swizzled layout.
+// Several "problems" (the five FPN levels, which share the head weights) are served by ONE launch.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace orp {
+namespace {
+
+constexpr int kMaxProb = 5;
+constexpr int kStagesMax = 6;
+constexpr int kBM = 128;
+constexpr int kBK = 64;                       // bf16 elements per K block = 128 bytes = one swizzle row
+constexpr int kABytes = kBM * kBK * 2;        // 16 KiB
+
+struct Problem {
+    int N, H, W, Ho, Wo;
+    int BW, BH, BI;                           // tile box: BW*BH*BI == 128 output pixels
+    int tiles_w, tiles_h, tiles_i, tile_start;
+    void *out;                                // bf16 or fp32 NHWC [N,Ho,Wo,Cout]
+    const __nv_bfloat16 *res;                 // optional residual, bf16 NHWC [N,Ho,Wo,Cout]
+    const float *res32;                       // optional fp32 residual (head: refine += init)
+    const __nv_bfloat16 *x;                   // activation base (deformable variant)
+    const float *offset;                      // deformable: [N,Ho,Wo,2*taps] fp32
+};
+
+struct alignas(64) TcParams {
+    CUtensorMap tmA[kMaxProb];
+    CUtensorMap tmB;
+    Problem prob[kMaxProb];
+    int nprob, num_m_tiles, n_tiles_n, num_tiles;
+    int KH, KW, Cin, cin_blocks, stride, pad, Cout, relu;
+    const float *bias;
+};
+
+// ----------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, %1;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(pred) : "r"(0xffffffffu));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_load_4d(void *smem, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *smem, const CUtensorMap *tm, uint64_t *bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, 128-byte swizzle: start address >> 4, LBO = 1 (ignored), SBO = 1024 B >> 4, version 1, layout 2
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Ring {
+    int stage = 0;
+    uint32_t phase = 0;
+    int n;
+    __device__ explicit Ring(int n_) : n(n_) {}
+    __device__ void next() { if (++stage == n) { stage = 0; phase ^= 1; } }
+};
+
+__device__ __forceinline__ void decode_tile(const TcParams &P, int tile, int &pi, int &wb, int &hb, int &ib, int &nt)
+{
+    nt = tile % P.n_tiles_n;
+    const int mt = tile / P.n_tiles_n;
+    pi = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxProb; ++k)
+        if (k < P.nprob && mt >= P.prob[k].tile_start) pi = k;
+    const Problem &pr = P.prob[pi];
+    const int local = mt - pr.tile_start;
+    wb = local % pr.tiles_w;
+    hb = (local / pr.tiles_w) % pr.tiles_h;
+    ib = local / (pr.tiles_w * pr.tiles_h);
+}
+
+// ----------------------------------------------------------------------------------------------- kernel
+// BN: accumulator width (32..256).  OUT_F32: fp32 output (head predictions) instead of bf16.
+// DEFORM: A operand produced by warps 6-9 (bilinear gather) instead of TMA.
+template <int BN, bool OUT_F32, bool DEFORM>
+__global__ void __launch_bounds__(DEFORM ? 320 : 192, 1)
+conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages][A 16K][B BN*128] | barriers
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kBBytes = BN * kBK * 2;
+    constexpr int kStageBytes = kABytes + kBBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)stages * kStageBytes);
+    uint64_t *full = bars;                       // [stages]  TMA bytes landed (+ producer arrivals when DEFORM)
+    uint64_t *empty = bars + kStagesMax;         // [stages]  MMA finished reading the stage
+    uint64_t *tfull = bars + 2 * kStagesMax;     // [2] accumulator ready
+    uint64_t *tempty = tfull + 2;                // [2] accumulator drained
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+    if (warp == 0 && elect_one()) {
+#pragma unroll 1
+        for (int p = 0; p < P.nprob; ++p)
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmA[p]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmB) : "memory");
+    }
+    if (warp == 1) {
+        if (elect_one()) {
+            for (int s = 0; s < stages; ++s) {
+                mbar_init(&full[s], DEFORM ? 1 + 128 : 1);
+                mbar_init(&empty[s], 1);
+            }
+            for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int kblocks = P.KH * P.KW * P.cin_blocks;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (elect_one()) {
+            Ring r(stages);
+            for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+                int pi, wb, hb, ib, nt;
+                decode_tile(P, tile, pi, wb, hb, ib, nt);
+                const Problem &pr = P.prob[pi];
+                const int w0 = wb * pr.BW * P.stride - P.pad, h0 = hb * pr.BH * P.stride - P.pad, i0 = ib * pr.BI;
+                for (int tap = 0; tap < P.KH * P.KW; ++tap) {
+                    const int kh = tap / P.KW, kw = tap - kh * P.KW;
+                    for (int cb = 0; cb < P.cin_blocks; ++cb) {
+                        mbar_wait(&empty[r.stage], r.phase ^ 1);
+                        uint8_t *sa = smem + (size_t)r.stage * kStageBytes;
+                        mbar_expect_tx(&full[r.stage], DEFORM ? kBBytes : kABytes + kBBytes);
+                        if (!DEFORM) tma_load_4d(sa, &P.tmA[pi], &full[r.stage], cb * kBK, w0 + kw, h0 + kh, i0);
+                        tma_load_2d(sa + kABytes, &P.tmB, &full[r.stage], (tap * P.cin_blocks + cb) * kBK, nt * BN);
+                        r.next();
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        Ring r(stages);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full[r.stage], r.phase);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = smem_u32(smem + (size_t)r.stage * kStageBytes);
+                    const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k)
+                        umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(&empty[r.stage]);
+                    if (kb == kblocks - 1) umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                r.next();
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp < 6) {
+        // ===================================================== epilogue (TMEM lane quarter = warp % 4)
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+            int pi, wb, hb, ib, nt;
+            decode_tile(P, tile, pi, wb, hb, ib, nt);
+            const Problem &pr = P.prob[pi];
+            const int rrow = q * 32 + lane;
+            const int iw = rrow % pr.BW, ih = (rrow / pr.BW) % pr.BH, ii = rrow / (pr.BW * pr.BH);
+            const int w = wb * pr.BW + iw, h = hb * pr.BH + ih, n = ib * pr.BI + ii;
+            const bool valid = (w < pr.Wo) && (h < pr.Ho) && (n < pr.N);
+            const size_t pix = ((size_t)n * pr.Ho + h) * pr.Wo + w;
+            mbar_wait(&tfull[acc], acc_phase);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
+                const int c0 = nt * BN + ch * 32;
+                if (valid && c0 < P.Cout) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    const bool full32 = (c0 + 32 <= P.Cout);
+                    if (P.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (full32 || c0 + j < P.Cout) f[j] += P.bias[c0 + j];
+                    }
+                    if (pr.res) {
+                        const __nv_bfloat16 *rp = pr.res + pix * P.Cout + c0;
+                        if (full32) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const uint4 u = *reinterpret_cast<const uint4 *>(rp + j4 * 8);
+                                const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162 *>(&uu[k]);
+                                    f[j4 * 8 + 2 * k] += __bfloat162float(b2.x);
+                                    f[j4 * 8 + 2 * k + 1] += __bfloat162float(b2.y);
+                                }
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j) if (c0 + j < P.Cout) f[j] += __bfloat162float(rp[j]);
+                        }
+                    }
+                    if (pr.res32) {
+                        const float *rp = pr.res32 + pix * P.Cout + c0;
+                        for (int j = 0; j < 32; ++j) if (c0 + j < P.Cout) f[j] += rp[j];
+                    }
+                    if (P.relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    if (OUT_F32) {
+                        float *op = reinterpret_cast<float *>(pr.out) + pix * P.Cout + c0;
+                        if (full32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4)
+                                *reinterpret_cast<float4 *>(op + j4 * 4) = make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
+                        } else {
+                            for (int j = 0; j < 32; ++j) if (c0 + j < P.Cout) op[j] = f[j];
+                        }
+                    } else {
+                        __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(pr.out) + pix * P.Cout + c0;
+                        if (full32) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    __nv_bfloat162 b2 = __floats2bfloat162_rn(f[j4 * 8 + 2 * k], f[j4 * 8 + 2 * k + 1]);
+                                    pk[k] = *reinterpret_cast<uint32_t *>(&b2);
+                                }
+                                *reinterpret_cast<uint4 *>(op + j4 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j) if (c0 + j < P.Cout) op[j] = __float2bfloat16_rn(f[j]);
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (DEFORM) {
+        // ===================================================== deformable A-operand producers (warps 6-9)
+        const int rrow = (warp - 6) * 32 + lane;          // one output pixel (= one smem row) per thread
+        Ring r(stages);
+        for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+            int pi, wb, hb, ib, nt;
+            decode_tile(P, tile, pi, wb, hb, ib, nt);
+            const Problem &pr = P.prob[pi];
+            const int iw = rrow % pr.BW, ih = (rrow / pr.BW) % pr.BH, ii = rrow / (pr.BW * pr.BH);
+            const int w = wb * pr.BW + iw, h = hb * pr.BH + ih, n = ib * pr.BI + ii;
+            const bool valid = (w < pr.Wo) && (h < pr.Ho) && (n < pr.N);
+            const __nv_bfloat16 *img = pr.x + (size_t)(valid ? n : 0) * pr.H * pr.W * P.Cin;
+            const float *offp = pr.offset + (((size_t)(valid ? n : 0) * pr.Ho + (valid ? h : 0)) * pr.Wo + (valid ? w : 0)) * (2 * P.KH * P.KW);
+            for (int tap = 0; tap < P.KH * P.KW; ++tap) {
+                const int kh = tap / P.KW, kw = tap - kh * P.KW;
+                // deformable_im2col_gpu_kernel (deform_conv_cuda_kernel.cu:216-237)
+                float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
+                const __nv_bfloat16 *p1 = img, *p2 = img, *p3 = img, *p4 = img;
+                if (valid) {
+                    const float h_im = (float)(h * P.stride - P.pad + kh) + offp[2 * tap];
+                    const float w_im = (float)(w * P.stride - P.pad + kw) + offp[2 * tap + 1];
+                    if (h_im > -1.f && w_im > -1.f && h_im < (float)pr.H && w_im < (float)pr.W) {
+                        const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                        const int h_high = h_low + 1, w_high = w_low + 1;
+                        const float lh = h_im - (float)h_low, lw = w_im - (float)w_low, hh = 1.f - lh, hw = 1.f - lw;
+                        if (h_low >= 0 && w_low >= 0) { w1 = hh * hw; p1 = img + ((size_t)h_low * pr.W + w_low) * P.Cin; }
+                        if (h_low >= 0 && w_high <= pr.W - 1) { w2 = hh * lw; p2 = img + ((size_t)h_low * pr.W + w_high) * P.Cin; }
+                        if (h_high <= pr.H - 1 && w_low >= 0) { w3 = lh * hw; p3 = img + ((size_t)h_high * pr.W + w_low) * P.Cin; }
+                        if (h_high <= pr.H - 1 && w_high <= pr.W - 1) { w4 = lh * lw; p4 = img + ((size_t)h_high * pr.W + w_high) * P.Cin; }
+                    }
+                }
+                for (int cb = 0; cb < P.cin_blocks; ++cb) {
+                    mbar_wait(&empty[r.stage], r.phase ^ 1);
+                    uint8_t *sa = smem + (size_t)r.stage * kStageBytes + (size_t)rrow * 128;
+#pragma unroll
+                    for (int c16 = 0; c16 < 8; ++c16) {
+                        const int co = cb * kBK + c16 * 8;
+                        const uint4 u1 = *reinterpret_cast<const uint4 *>(p1 + co), u2 = *reinterpret_cast<const uint4 *>(p2 + co);
+                        const uint4 u3 = *reinterpret_cast<const uint4 *>(p3 + co), u4 = *reinterpret_cast<const uint4 *>(p4 + co);
+                        const uint32_t a1[4] = {u1.x, u1.y, u1.z, u1.w}, a2[4] = {u2.x, u2.y, u2.z, u2.w};
+                        const uint32_t a3[4] = {u3.x, u3.y, u3.z, u3.w}, a4[4] = {u4.x, u4.y, u4.z, u4.w};
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a1[k]));
+                            const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a2[k]));
+                            const float2 f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a3[k]));
+                            const float2 f4 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a4[k]));
+                            const float vx = w1 * f1.x + w2 * f2.x + w3 * f3.x + w4 * f4.x;
+                            const float vy = w1 * f1.y + w2 * f2.y + w3 * f3.y + w4 * f4.y;
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(vx, vy);
+                            pk[k] = *reinterpret_cast<uint32_t *>(&b2);
+                        }
+                        // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
+                        *reinterpret_cast<uint4 *>(sa + ((c16 ^ (rrow & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy (UMMA reads smem)
+                    mbar_arrive(&full[r.stage]);
+                    r.next();
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+
+template <int BN, bool OUT_F32, bool DEFORM>
+int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st)
+{
+    const size_t smem = 1024 + (size_t)stages * (kABytes + BN * kBK * 2) + 256;
+    auto kern = conv_tc_kernel<BN, OUT_F32, DEFORM>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ORP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    kern<<<grid, DEFORM ? 320 : 192, smem, st>>>(P, stages);
+    ORP_LAUNCHED();
+    return ORP_OK;
+}
+
+}  // namespace
+}  // namespace orp
+
+using namespace orp;
+
+/* see include/orp_b200.h */
+extern "C" int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const void *w, int Cout, int Cout_padded, int KH,
+                               int KW, int Cin, int stride, int pad, const float *bias, int relu, int out_f32,
+                               int deform, void *stream)
+{
+    if (nprob < 1 || nprob > kMaxProb || !probs || !w) return fail(ORP_EINVAL, "conv2d_bf16: bad arguments");
+    if (Cin % kBK) return fail(ORP_EINVAL, "conv2d_bf16: Cin must be a multiple of 64");
+    if (Cout_padded % 32 || Cout_padded < Cout) return fail(ORP_EINVAL, "conv2d_bf16: padded Cout must be a multiple of 32");
+    int rc = ensure_device();
+    if (rc) return rc;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(ORP_ECUDA, "conv2d_bf16: cuTensorMapEncodeTiled unavailable");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    int BN = 256;
+    if (Cout_padded % 256) BN = (Cout_padded % 128 == 0) ? 128 : (Cout_padded % 64 == 0) ? 64 : 32;
+    TcParams P;
+    memset(&P, 0, sizeof(P));
+    P.nprob = nprob; P.KH = KH; P.KW = KW; P.Cin = Cin; P.cin_blocks = Cin / kBK; P.stride = stride; P.pad = pad;
+    P.Cout = Cout; P.relu = relu; P.bias = bias;
+    P.n_tiles_n = Cout_padded / BN;
+    int mt = 0;
+    for (int i = 0; i < nprob; ++i) {
+        const orp_tc_problem &q = probs[i];
+        Problem &pr = P.prob[i];
+        pr.N = q.N; pr.H = q.H; pr.W = q.W;
+        pr.Ho = (q.H + 2 * pad - (KH - 1) - 1) / stride + 1;
+        pr.Wo = (q.W + 2 * pad - (KW - 1) - 1) / stride + 1;
+        if (pr.Ho <= 0 || pr.Wo <= 0 || !q.x || !q.out) return fail(ORP_EINVAL, "conv2d_bf16: bad problem");
+        pr.BW = pow2_floor(pr.Wo < 128 ? pr.Wo : 128);
+        if (stride * pr.BW > 256) pr.BW = 256 / stride;
+        pr.BH = pow2_floor(pr.Ho < 128 / pr.BW ? pr.Ho : 128 / pr.BW);
+        pr.BI = 128 / (pr.BW * pr.BH);
+        pr.tiles_w = ceil_div(pr.Wo, pr.BW); pr.tiles_h = ceil_div(pr.Ho, pr.BH); pr.tiles_i = ceil_div(pr.N, pr.BI);
+        pr.tile_start = mt;
+        mt += pr.tiles_w * pr.tiles_h * pr.tiles_i;
+        pr.out = q.out; pr.res = static_cast<const __nv_bfloat16 *>(q.residual_bf16); pr.res32 = q.residual_f32;
+        pr.x = static_cast<const __nv_bfloat16 *>(q.x); pr.offset = q.offset;
+        if (deform && !q.offset) return fail(ORP_EINVAL, "conv2d_bf16: deformable conv needs offsets");
+        if (!deform) {
+            cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.N};
+            cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)q.W * Cin * 2, (cuuint64_t)q.H * q.W * Cin * 2};
+            cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(pr.BW * stride), (cuuint32_t)(pr.BH * stride), (cuuint32_t)pr.BI};
+            cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+            CUresult r = enc(&P.tmA[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(q.x), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_bf16: cuTensorMapEncodeTiled(A) failed");
+        }
+    }
+    {
+        const cuuint64_t K = (cuuint64_t)KH * KW * Cin;
+        cuuint64_t gdim[2] = {K, (cuuint64_t)Cout_padded};
+        cuuint64_t gstr[1] = {K * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&P.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(w), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_bf16: cuTensorMapEncodeTiled(B) failed");
+    }
+    P.num_m_tiles = mt;
+    P.num_tiles = mt * P.n_tiles_n;
+    int sms = 148;
+    {
+        int dev = 0;
+        ORP_CUDA(cudaGetDevice(&dev));
+        ORP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int grid = P.num_tiles < sms ? P.num_tiles : sms;
+    const int stage_bytes = kABytes + BN * kBK * 2;
+    int stages = (int)((227 * 1024 - 2048) / stage_bytes);
+    if (stages > kStagesMax) stages = kStagesMax;
+#define ORP_TC_DISPATCH(BNV)                                                                     \
+    if (BN == BNV) {                                                                             \
+        if (deform) return out_f32 ? launch_tc<BNV, true, true>(P, stages, grid, st) : launch_tc<BNV, false, true>(P, stages, grid, st); \
+        return out_f32 ? launch_tc<BNV, true, false>(P, stages, grid, st) : launch_tc<BNV, false, false>(P, stages, grid, st);          \
+    }
+    ORP_TC_DISPATCH(256)
+    ORP_TC_DISPATCH(128)
+    ORP_TC_DISPATCH(64)
+    ORP_TC_DISPATCH(32)
+#undef ORP_TC_DISPATCH
+    return fail(ORP_EINVAL, "conv2d_bf16: unsupported tile width");
+}

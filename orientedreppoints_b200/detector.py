@@ -25,6 +25,7 @@ class ConvLayer:
 
     def __init__(self, w_nchw, bias, stride, pad, device, pad_cin_to=None):
         w = w_nchw.permute(0, 2, 3, 1).contiguous()                   # [Cout, KH, KW, Cin]
+        self.w_raw = w.float().cpu()                                  # unpadded, for the tensor-core operand prep
         if pad_cin_to is not None and w.shape[3] < pad_cin_to:
             w = torch.cat([w, w.new_zeros(*w.shape[:3], pad_cin_to - w.shape[3])], 3).contiguous()
         self.cout, self.kh, self.kw, self.cin = w.shape
@@ -81,6 +82,20 @@ class EngineF32:
         y, st = self.conv(x, L, want_stats=True)
         return self.gn(y, st, norm, relu=relu, up=up)
 
+    # multi-level forms (the head's weights are shared by the five FPN levels)
+    def conv_multi(self, xs, L, relu=False, residual=None, out_f32=False, residual_f32=None):
+        res = residual if residual is not None else residual_f32
+        return [self.conv(x, L, relu=relu, residual=None if res is None else res[i]) for i, x in enumerate(xs)]
+
+    def conv_gn_multi(self, xs, L, norm, relu=False):
+        return [self.conv_gn(x, L, norm, relu=relu) for x in xs]
+
+    def deform_conv_multi(self, xs, offsets, L, relu=False):
+        return [self.deform_conv(x, o, L, relu=relu) for x, o in zip(xs, offsets)]
+
+    def stem(self, x, L):
+        return self.conv(x, L, relu=True)
+
     def maxpool(self, x):
         n, h, w, c = x.shape
         ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
@@ -97,9 +112,6 @@ class EngineF32:
                                             _lib.ptr(y), _lib.current_stream_ptr())
         _lib.check(rc, "orp_deform_conv2d_f32")
         return y
-
-    def to_f32(self, x):
-        return x
 
 
 class OrientedRepPointsDetector:
@@ -166,7 +178,7 @@ class OrientedRepPointsDetector:
     def extract_feat(self, img):
         e = self.eng
         x = e.prepare_input(img)
-        x = e.maxpool(e.conv(x, self.stem, relu=True))
+        x = e.maxpool(e.stem(x, self.stem))
         feats = []
         for stage in self.blocks:
             for blk in stage:
@@ -184,23 +196,25 @@ class OrientedRepPointsDetector:
         outs.append(e.conv_gn(outs[-1], *self.fpn[4]))
         return outs
 
-    def head_single(self, x, gradient_mul=0.3):
+    def head(self, feats, gradient_mul=0.3):
+        """forward_single (orientedreppoints_head.py:148-171) for all levels at once: the weights are shared,
+        so every layer is ONE launch over the five levels.  Returns per level (cls, init, refine), fp32 NHWC."""
         e = self.eng
-        cf, pf = x, x
+        cf, pf = list(feats), list(feats)
         for (lc, nc), (lr, nr) in zip(self.cls_convs, self.reg_convs):
-            cf = e.conv_gn(cf, lc, nc, relu=True)
-            pf = e.conv_gn(pf, lr, nr, relu=True)
-        init = e.to_f32(e.conv(e.conv(pf, self.init_conv, relu=True), self.init_out))       # [N,H,W,18] fp32
+            cf = e.conv_gn_multi(cf, lc, nc, relu=True)
+            pf = e.conv_gn_multi(pf, lr, nr, relu=True)
+        init = e.conv_multi(e.conv_multi(pf, self.init_conv, relu=True), self.init_out, out_f32=True)   # [N,H,W,18]
         # head :162-163, evaluated in fp32 exactly as written there
-        offset = ((1 - gradient_mul) * init + gradient_mul * init) - self.dcn_base_offset
-        offset = offset.contiguous()
-        cls = e.conv(e.deform_conv(cf, offset, self.cls_dcn, relu=True), self.cls_out)
-        ref = e.conv(e.deform_conv(pf, offset, self.ref_dcn, relu=True), self.ref_out, residual=init)
-        return e.to_f32(cls), init, e.to_f32(ref)
+        offsets = [(((1 - gradient_mul) * t + gradient_mul * t) - self.dcn_base_offset).contiguous() for t in init]
+        cls = e.conv_multi(e.deform_conv_multi(cf, offsets, self.cls_dcn, relu=True), self.cls_out, out_f32=True)
+        ref = e.conv_multi(e.deform_conv_multi(pf, offsets, self.ref_dcn, relu=True), self.ref_out, out_f32=True,
+                           residual_f32=init)
+        return [(c.float(), i, r.float()) for c, i, r in zip(cls, init, ref)]
 
     def forward_dense(self, img):
         feats = self.extract_feat(img)
-        return [self.head_single(f) for f in feats], feats
+        return self.head(feats), feats
 
     # ------------------------------------------------------------------ simple_test
     def simple_test(self, img, img_metas=None, rescale=True, return_tensors=False):

@@ -95,3 +95,76 @@ def test_simple_test_matches_reference_pipeline(cuda, sd):
     assert torch.equal(labels.cpu(), rl)                                    # index work: bit-exact
     assert float((dets.cpu() - rd).abs().max()) < 1e-3                      # coordinates in pixels (1e-4 * stride scale)
     assert torch.equal(dets[:, -1].cpu(), rd[:, -1])                        # scores
+
+
+# ------------------------------------------------------------------------------- tensor-core engine
+def _bf16_ref_conv(x, wt, b, s, p):
+    """fp64 conv over the bf16-ROUNDED operands: what an exact accumulation of the tensor-core inputs gives"""
+    import torch.nn.functional as F
+    return F.conv2d(x.bfloat16().double(), wt.bfloat16().double(), None if b is None else b.double(), s, p)
+
+
+@pytest.mark.parametrize("cin,cout,k,s,p,h,w,n", [
+    (64, 64, 1, 1, 0, 32, 32, 1),        # one tile, one K block
+    (64, 256, 1, 1, 0, 64, 64, 2),       # BN=256
+    (256, 64, 3, 1, 1, 64, 64, 1),       # 3x3: TMA zero padding, 36 K blocks
+    (128, 128, 3, 2, 1, 64, 64, 2),      # stride 2 through tensor-map element strides
+    (512, 1024, 1, 2, 0, 32, 32, 2),     # 1x1 stride 2 (downsample), 4 N tiles
+    (256, 256, 3, 1, 1, 37, 53, 2),      # ragged: partial tiles in W and H
+    (256, 18, 1, 1, 0, 19, 23, 3),       # Cout 18 -> padded to 32, masked stores
+    (256, 256, 3, 2, 1, 16, 16, 3),      # 8x8 output: tile spans 2 images
+    (2048, 256, 3, 2, 1, 32, 32, 1),     # P6: K = 18432
+])
+def test_conv_tc_vs_exact(cuda, cin, cout, k, s, p, h, w, n):
+    from orientedreppoints_b200.detector import ConvLayer
+    from orientedreppoints_b200.engine_tc import EngineTC
+    e = EngineTC(cuda)
+    g = torch.Generator().manual_seed(cin + cout + k + h)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) * (1.0 / (cin * k * k) ** 0.5)
+    b = torch.randn(cout, generator=g)
+    ref = _bf16_ref_conv(x, wt, b, s, p).float()
+    L = ConvLayer(wt, b, s, p, cuda)
+    xb = x.permute(0, 2, 3, 1).contiguous().to(cuda, torch.bfloat16)
+    y32 = e.conv(xb, L, out_f32=True)
+    assert _rel(_nchw(y32).cpu(), ref) < 2e-5, "fp32 accumulation of exact bf16 products"
+    r = torch.randn(ref.shape, generator=g)
+    yb = e.conv(xb, L, relu=True, residual=r.permute(0, 2, 3, 1).contiguous().to(cuda, torch.bfloat16))
+    refb = torch.relu(ref + r.bfloat16().float())
+    assert _rel(_nchw(yb.float()).cpu(), refb) < 6e-3          # one bf16 rounding of the output (2^-8)
+
+
+def test_deform_conv_tc_vs_f32_engine(cuda):
+    from oracle import torch_reference as tr
+    from orientedreppoints_b200.detector import ConvLayer
+    from orientedreppoints_b200.engine_tc import EngineTC
+    e = EngineTC(cuda)
+    g = torch.Generator().manual_seed(3)
+    xs, offs, refs = [], [], []
+    wt = torch.randn(256, 256, 3, 3, generator=g) * 0.02
+    for (h, w) in [(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)]:       # five "levels" in one launch
+        x = torch.randn(2, 256, h, w, generator=g)
+        off = torch.randn(2, 18, h, w, generator=g) * 2.5
+        refs.append(tr.deform_conv_ref(x.bfloat16().double(), off.double(), wt.bfloat16().double()).float())
+        xs.append(x.permute(0, 2, 3, 1).contiguous().to(cuda, torch.bfloat16))
+        offs.append(off.permute(0, 2, 3, 1).contiguous().to(cuda))
+    L = ConvLayer(wt, None, 1, 1, cuda)
+    ys = e.deform_conv_multi(xs, offs, L)
+    for y, ref in zip(ys, refs):
+        # sampled values are rounded to bf16 before the MMA (2^-9 relative each), outputs to bf16
+        assert _rel(_nchw(y.float()).cpu(), ref) < 1.5e-2
+
+
+def test_dense_graph_bf16_vs_f32_engine(cuda, sd):
+    from orientedreppoints_b200.detector import OrientedRepPointsDetector
+    d32 = OrientedRepPointsDetector(sd, 50, cuda, "fp32")
+    d16 = OrientedRepPointsDetector(sd, 50, cuda, "bf16")
+    img = torch.randn(2, 3, 256, 320, generator=torch.Generator().manual_seed(1)).to(cuda)
+    o32, f32 = d32.forward_dense(img)
+    o16, f16 = d16.forward_dense(img)
+    for lvl in range(5):
+        assert _rel(f16[lvl].float(), f32[lvl]) < 0.06, lvl          # bf16 activations through ~60 layers
+        for k in range(3):
+            a, b = o16[lvl][k], o32[lvl][k]
+            assert a.shape == b.shape and a.dtype == torch.float32
+            assert float((a - b).abs().max()) < 0.08 * max(1.0, float(b.abs().max())), (lvl, k)

@@ -114,6 +114,10 @@ int orp_rnms_last_stats(orp_nms_stats *out);
  * returns the elapsed device time of that kernel for the last call of this thread. */
 void orp_set_timing(int on);
 int orp_rnms_last_sweep_ms(float *ms);
+/* with timing on, every tensor-core convolution launch is bracketed the same way; this collects (and
+ * resets) the summed device time, the number of launches and their algorithmic FLOPs (2*MACs) since
+ * the previous collect on this thread */
+int orp_tc_timing_collect(float *total_ms, int *launches, double *flops);
 
 /* ------------------------------------------------------------------------------------------
  * Pairwise rotated IoU

@@ -45,6 +45,7 @@ SIGNATURES = {
     "orp_rnms_last_stats": (_i, [ctypes.POINTER(NmsStats)]),
     "orp_set_timing": (None, [_i]),
     "orp_rnms_last_sweep_ms": (_i, [ctypes.POINTER(ctypes.c_float)]),
+    "orp_tc_timing_collect": (_i, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), ctypes.POINTER(_d)]),
     "orp_poly_overlaps_host": (_i, [_vp, _vp, _vp, _i, _i, _i]),
     "orp_poly_overlaps": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "orp_quad_iou_matrix": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),
@@ -114,6 +115,12 @@ def last_sweep_ms():
     v = ctypes.c_float(0)
     check(lib().orp_rnms_last_sweep_ms(ctypes.byref(v)), "orp_rnms_last_sweep_ms")
     return float(v.value)
+
+
+def tc_timing_collect():
+    ms, n, fl = ctypes.c_float(0), ctypes.c_int(0), ctypes.c_double(0)
+    check(lib().orp_tc_timing_collect(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)), "orp_tc_timing_collect")
+    return float(ms.value), int(n.value), float(fl.value)
 
 
 def current_stream_ptr():

@@ -1,0 +1,153 @@
+"""Tile-throughput workload of bench.py: BASELINE.json configs[1] - R-50 + FPN + OrientedRepPointsHead on
+synthetic 1024x1024 tiles, random-init weights, one process per GPU, tiles sharded across ranks (weak
+scaling: `batch` tiles per GPU per step), ONE all-gather of the per-tile detections per step when N > 1.
+
+score_thr is set to 0: with random-init weights every sigmoid score is ~0.01 < 0.05 and the
+config-faithful run would hand an empty set to NMS; with 0 every tile feeds 80 160 candidates to
+multiclass_rnms, which is the load BASELINE.json describes ("~10^5 proposals per tile").
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from .core.transforms import rbbox2result
+from .detector import OrientedRepPointsDetector
+from .weights import STAGE_BLOCKS, random_state_dict
+
+
+def conv_flops_per_tile(depth=50, size=1024):
+    """2*MACs of every convolution (dense or deformable) of the graph for one size x size tile."""
+    fl = 0.0
+    s = size // 2
+    fl += 2.0 * s * s * 64 * 147                                       # conv1 7x7/2
+    s //= 2                                                            # maxpool
+    inpl = 64
+    for li, (nblk, planes) in enumerate(zip(STAGE_BLOCKS[depth], (64, 128, 256, 512))):
+        for b in range(nblk):
+            st = 2 if (b == 0 and li > 0) else 1
+            so = s // st
+            fl += 2.0 * s * s * planes * inpl                          # conv1 1x1 (input resolution)
+            fl += 2.0 * so * so * planes * planes * 9                  # conv2 3x3 (stride here: style='pytorch')
+            fl += 2.0 * so * so * planes * 4 * planes                  # conv3 1x1
+            if b == 0:
+                fl += 2.0 * so * so * planes * 4 * inpl                # downsample
+            inpl = planes * 4
+            s = so
+    lv = [size // 8, size // 16, size // 32, size // 64, size // 128]
+    for hw, cin in zip(lv[:3], (512, 1024, 2048)):
+        fl += 2.0 * hw * hw * 256 * cin                                # laterals
+        fl += 2.0 * hw * hw * 256 * 256 * 9                            # fpn convs
+    fl += 2.0 * lv[3] * lv[3] * 256 * 2048 * 9                         # P6 on C5
+    fl += 2.0 * lv[4] * lv[4] * 256 * 256 * 9                          # P7
+    loc = sum(h * h for h in lv)
+    per_loc = 2.0 * (6 * 256 * 256 * 9 + 256 * 256 * 9 + 256 * 18 + 2 * 256 * 256 * 9 + 256 * 15 + 256 * 18)
+    fl += loc * per_loc
+    return fl
+
+
+def run(args, rank, world, local, benchmod):
+    dev = torch.device("cuda", local)
+    batch = args.batch or 4
+    precision = args.precision or "bf16"
+    depth = 50
+    sd = random_state_dict(depth, seed=0, reference_init=True)
+    det = OrientedRepPointsDetector(sd, depth, dev, precision, test_cfg=dict(score_thr=0.0))
+    g = torch.Generator().manual_seed(1000 + rank)
+    img_host = torch.randn(batch, 3, 1024, 1024, generator=g).pin_memory()
+    img = img_host.to(dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    warm = max(args.warmup, 3)
+
+    def step_device():
+        return det.simple_test(img, return_tensors=True)
+
+    def gather(results):
+        """fixed-layout detection buffer [batch, 2000, 28] (27 + label) + counts, ONE all_gather"""
+        buf = torch.zeros((batch, 2000, 28), dtype=torch.float32, device=dev)
+        cnt = torch.zeros((batch,), dtype=torch.int32, device=dev)
+        for i, (d, l) in enumerate(results):
+            k = d.shape[0]
+            buf[i, :k, :27] = d
+            buf[i, :k, 27] = l.float()
+            cnt[i] = k
+        if world > 1:
+            import torch.distributed as dist
+            allb = torch.empty((world,) + tuple(buf.shape), dtype=buf.dtype, device=dev)
+            allc = torch.empty((world, batch), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(allb, buf)
+            dist.all_gather_into_tensor(allc, cnt)
+            return allb, allc
+        return buf, cnt
+
+    for _ in range(warm):
+        gather(step_device())
+    benchmod.barrier(world)
+    sampler = benchmod.ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.set_timing(precision == "bf16")
+    _lib.tc_timing_collect()
+    _lib.reset_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    benchmod.barrier(world)
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)
+        ev[s][0].record()
+        res = step_device()
+        gather(res)
+        ev[s][1].record()
+    benchmod.barrier(world)
+    launches = _lib.launch_count()
+    tc_ms, tc_launches, tc_flops = _lib.tc_timing_collect() if precision == "bf16" else (0.0, 0, 0.0)
+    _lib.set_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = benchmod.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), world)
+    ms_step = total_ms / args.steps
+    ndet = [int(r[0].shape[0]) for r in res]
+
+    # end to end through the public API: pinned host tiles -> H2D -> simple_test -> rbbox2result (D2H)
+    def step_e2e():
+        x = img_host.to(dev, non_blocking=True)
+        r = det.simple_test(x, return_tensors=True)
+        gather(r)
+        return [rbbox2result(d, l, 16) for d, l in r]
+
+    for _ in range(2):
+        step_e2e()
+    benchmod.barrier(world)
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = step_e2e()
+    torch.cuda.synchronize()
+    e2e_ms = benchmod.max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps, world)
+    d2h = sum(int(a.nbytes) for per_img in out for a in per_img)
+
+    pk = benchmod.peaks()
+    fl_tile = conv_flops_per_tile(depth)
+    line = {
+        "metric": "1024x1024 tiles/sec", "value": world * batch / (ms_step * 1e-3), "unit": "tiles/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": precision, "data": "synthetic",
+        "config": {"workload": "R-%d FPN OrientedRepPoints, %d synthetic 1024x1024 tile(s) per GPU per step, random-init "
+                               "weights, score_thr=0 (80160 NMS candidates per tile), rnms iou 0.4, max_per_img 2000" % (depth, batch),
+                   "tiles_per_gpu_per_step": batch, "detections_per_tile": ndet[:4],
+                   "l2": "512 MiB flush write between timed steps", "gflop_per_tile": fl_tile / 1e9,
+                   "gather": "one all_gather_into_tensor of [tiles,2000,28] fp32 + counts per step" if world > 1 else "single rank"},
+        "gpu_launches": int(launches),
+        "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "tiles/s", "h2d_bytes_per_step": int(img_host.nbytes),
+                "d2h_bytes_per_step": int(d2h), "api": "OrientedRepPointsDetector.simple_test(img) -> rbbox2result lists"},
+    }
+    if precision == "bf16" and tc_ms > 0:
+        ach = tc_flops / (tc_ms * 1e-3) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "conv_tc_kernel (all %d launches per step)" % (tc_launches // args.steps),
+                            "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                            "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
+                            "algorithmic_flops_per_step": tc_flops / args.steps, "kernel_ms_per_step": tc_ms / args.steps,
+                            "kernel_share_of_step": (tc_ms / args.steps) / ms_step,
+                            "whole_step_tflops": batch * fl_tile / (ms_step * 1e-3) / 1e12}
+    if clocks is not None:
+        line["clocks"] = clocks
+    return line

@@ -12,6 +12,7 @@ namespace orp {
 
 extern thread_local char g_err[512];
 extern int64_t g_launches;
+extern int g_timing;                     // orp_set_timing(): bracket dominant kernels with CUDA events
 
 inline int fail(int code, const char *fmt, const char *a = "", const char *b = "")
 {

@@ -448,6 +448,12 @@ EncodeTiledFn encode_fn()
 
 int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 
+// event pool for orp_set_timing(1): every conv_tc launch is bracketed on its own stream
+constexpr int kEvPool = 1024;
+thread_local cudaEvent_t g_tc_ev[kEvPool][2];
+thread_local int g_tc_ev_created = 0, g_tc_ev_used = 0;
+thread_local double g_tc_flops = 0.0;
+
 template <int BN, bool OUT_F32, bool DEFORM>
 int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st)
 {
@@ -458,8 +464,23 @@ int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st)
         ORP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
+    int slot = -1;
+    if (g_timing && g_tc_ev_used < kEvPool) {
+        slot = g_tc_ev_used++;
+        if (slot >= g_tc_ev_created) {
+            ORP_CUDA(cudaEventCreate(&g_tc_ev[slot][0]));
+            ORP_CUDA(cudaEventCreate(&g_tc_ev[slot][1]));
+            g_tc_ev_created = slot + 1;
+        }
+        ORP_CUDA(cudaEventRecord(g_tc_ev[slot][0], st));
+        double fl = 0;
+        for (int i = 0; i < P.nprob; ++i)
+            fl += 2.0 * P.prob[i].N * P.prob[i].Ho * P.prob[i].Wo * (double)P.Cout * P.KH * P.KW * P.Cin;
+        g_tc_flops += fl;
+    }
     kern<<<grid, DEFORM ? 320 : 192, smem, st>>>(P, stages);
     ORP_LAUNCHED();
+    if (slot >= 0) ORP_CUDA(cudaEventRecord(g_tc_ev[slot][1], st));
     return ORP_OK;
 }
 
@@ -467,6 +488,21 @@ int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st)
 }  // namespace orp
 
 using namespace orp;
+
+extern "C" int orp_tc_timing_collect(float *total_ms, int *launches, double *flops)
+{
+    if (!total_ms || !launches || !flops) return fail(ORP_EINVAL, "orp_tc_timing_collect: null");
+    float sum = 0.f;
+    for (int i = 0; i < g_tc_ev_used; ++i) {
+        float ms = 0.f;
+        ORP_CUDA(cudaEventSynchronize(g_tc_ev[i][1]));
+        ORP_CUDA(cudaEventElapsedTime(&ms, g_tc_ev[i][0], g_tc_ev[i][1]));
+        sum += ms;
+    }
+    *total_ms = sum; *launches = g_tc_ev_used; *flops = g_tc_flops;
+    g_tc_ev_used = 0; g_tc_flops = 0.0;
+    return ORP_OK;
+}
 
 /* see include/orp_b200.h */
 extern "C" int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const void *w, int Cout, int Cout_padded, int KH,

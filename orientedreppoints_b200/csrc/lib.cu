@@ -5,6 +5,7 @@ namespace orp {
 
 thread_local char g_err[512] = "";
 int64_t g_launches = 0;
+int g_timing = 0;
 
 int ensure_device()
 {
@@ -32,6 +33,7 @@ int ensure_device()
 }  // namespace orp
 
 extern "C" const char *orp_last_error(void) { return orp::g_err; }
+extern "C" void orp_set_timing(int on) { orp::g_timing = on; }
 extern "C" int orp_version(void) { return 100; }
 extern "C" int orp_compiled_sm(void) { return 100; }
 extern "C" int64_t orp_launch_count(void) { return __atomic_load_n(&orp::g_launches, __ATOMIC_RELAXED); }

@@ -33,7 +33,6 @@ struct NmsCounters {
 };
 
 static thread_local orp_nms_stats g_last_stats;
-static int g_timing = 0;                                   // orp_set_timing()
 static thread_local cudaEvent_t g_ev[2] = {nullptr, nullptr};
 static thread_local NmsCounters *g_stats_dev = nullptr;   // device copy of the last call
 static thread_local NmsCounters *g_stats_pinned = nullptr;
@@ -592,8 +591,6 @@ extern "C" int orp_rnms(const float *dets, const int32_t *segments, int n, doubl
     return orp::run_nms(dets, segments, n, iou_thr, iou_mode, union_mode, order, keep_out, num_out,
                         static_cast<cudaStream_t>(stream));
 }
-
-extern "C" void orp_set_timing(int on) { orp::g_timing = on; }
 
 extern "C" int orp_rnms_last_sweep_ms(float *ms)
 {

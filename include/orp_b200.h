@@ -168,6 +168,26 @@ int orp_minarearect(const float *pts, int n, float *out, int32_t *hull_map, floa
                     const float *center, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Head post-processing
+ * ---------------------------------------------------------------------------------------- */
+
+/* OrientedRepPointsHead.get_bboxes + multiclass_rnms for a whole batch, device resident
+ * (mmdet/models/anchor_heads/orientedreppoints_head.py:673-779,
+ *  mmdet/core/post_processing/bbox_nms.py:93-182).
+ *   cls[l]   device fp32 NHWC [B, H[l], W[l], num_cls] logits (sigmoid classification)
+ *   ref[l]   device fp32 NHWC [B, H[l], W[l], 18] refined points, (dy,dx) interleaved, stride units
+ *   scale_factor  device fp32 [B] or NULL (= 1): boxes and points are divided by it (rescale=True)
+ *   dets_out   device fp32 [B, max_per_img, 27] rows = reppoints(18) | box(8) | score, zero padded
+ *   labels_out device int64 [B, max_per_img] (0-based class, -1 padding);  counts_out device int32 [B]
+ * Per level top-k(nms_pre) on the max class score (ties: lower location first), class-aware NMS by
+ * segment id instead of the coordinate-offset trick of bbox_nms.py:156-158, survivors in candidate
+ * order unless more than max_per_img survive, then the max_per_img best by score.  Asynchronous. */
+int orp_head_postprocess(int nlevels, const float *const *cls, const float *const *ref, const int *H,
+                         const int *W, const int *stride, int B, int num_cls, int nms_pre, float score_thr,
+                         double iou_thr, int max_per_img, const float *scale_factor, float *dets_out,
+                         int64_t *labels_out, int32_t *counts_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Dense layers, fp32 (CUDA cores) - the parity arithmetic of the backbone / FPN / head
  * All activations are NHWC ("channels last") contiguous device tensors; weights are
  * [Cout][KH][KW][Cin] (the reference's [Cout][Cin][KH][KW] permuted once at load time).

@@ -55,6 +55,39 @@ def get_bboxes_single(cls_scores, points_preds, strides, scale_factor, cfg, resc
     return mlvl_bboxes, mlvl_scores
 
 
+def get_bboxes_fused(cls_scores, pts_preds_refine, strides, img_metas, cfg, rescale=False):
+    """The same computation as get_bboxes() as ONE device-resident pipeline (orp_head_postprocess): returns
+    padded (dets [B,max_per_img,27], labels [B,max_per_img], counts [B]) device tensors, no host sync."""
+    import ctypes
+
+    from .. import _lib
+    n = len(cls_scores)
+    b = cls_scores[0].shape[0]
+    dev = cls_scores[0].device
+    cls_c = [c.contiguous() for c in cls_scores]
+    ref_c = [p.contiguous() for p in pts_preds_refine]
+    pa = (ctypes.c_void_p * n)(*[c.data_ptr() for c in cls_c])
+    pr = (ctypes.c_void_p * n)(*[p.data_ptr() for p in ref_c])
+    hs = (ctypes.c_int * n)(*[c.shape[1] for c in cls_c])
+    ws = (ctypes.c_int * n)(*[c.shape[2] for c in cls_c])
+    ss = (ctypes.c_int * n)(*[int(s) for s in strides])
+    cap = int(cfg['max_per_img'])
+    dets = torch.empty((b, cap, 27), dtype=torch.float32, device=dev)
+    labels = torch.empty((b, cap), dtype=torch.int64, device=dev)
+    counts = torch.empty((b,), dtype=torch.int32, device=dev)
+    sf = None
+    if rescale:
+        sf = torch.tensor([float(m['scale_factor']) for m in img_metas], dtype=torch.float32).to(dev, non_blocking=True)
+    nms_cfg = cfg['nms']
+    assert nms_cfg.get('type', 'rnms') == 'rnms'
+    with torch.cuda.device(dev):
+        rc = _lib.lib().orp_head_postprocess(n, pa, pr, hs, ws, ss, b, cls_c[0].shape[3], int(cfg.get('nms_pre', -1)),
+                                             float(cfg['score_thr']), float(nms_cfg['iou_thr']), cap, _lib.ptr(sf),
+                                             _lib.ptr(dets), _lib.ptr(labels), _lib.ptr(counts), _lib.current_stream_ptr())
+    _lib.check(rc, "orp_head_postprocess")
+    return dets, labels, counts
+
+
 def get_bboxes(cls_scores, pts_preds_refine, strides, img_metas, cfg, rescale=False, nms=True):
     """cls_scores[l]: [N,H,W,15]; pts_preds_refine[l]: [N,H,W,18] -> list of (dets [k,27], labels [k])"""
     out = []

@@ -25,6 +25,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -41,7 +42,8 @@ constexpr int kABytes = kBM * kBK * 2;        // 16 KiB
 
 struct Problem {
     int N, H, W, Ho, Wo;
-    int BW, BH, BI;                           // tile box: BW*BH*BI == 128 output pixels
+    int BW, BH, BI;                           // tile box: BW*BH*BI == 128 output pixels (powers of two)
+    int lbw, lbh;                             // log2(BW), log2(BH)
     int tiles_w, tiles_h, tiles_i, tile_start;
     void *out;                                // bf16 or fp32 NHWC [N,Ho,Wo,Cout]
     const __nv_bfloat16 *res;                 // optional residual, bf16 NHWC [N,Ho,Wo,Cout]
@@ -180,16 +182,21 @@ __global__ void __launch_bounds__(DEFORM ? 320 : 192, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [stages][A 16K][B BN*128] | barriers
+    // dynamic: [stages][A 16K | B BN*128]  then the epilogue staging tile [128 rows][HC*2 + 16 B]
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kBBytes = BN * kBK * 2;
     constexpr int kStageBytes = kABytes + kBBytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)stages * kStageBytes);
+    constexpr int HC = BN < 64 ? BN : 64;              // columns staged per epilogue pass
+    constexpr int kPitch = HC * 2 + 16;                // bytes per staged row (+16: conflict-free 16-byte accesses)
+    uint8_t *stage_out = smem + (size_t)stages * kStageBytes;
+    __shared__ uint64_t bars[2 * kStagesMax + 4];
+    __shared__ float s_bias[256];
+    __shared__ uint32_t tmem_slot_s;
     uint64_t *full = bars;                       // [stages]  TMA bytes landed (+ producer arrivals when DEFORM)
     uint64_t *empty = bars + kStagesMax;         // [stages]  MMA finished reading the stage
     uint64_t *tfull = bars + 2 * kStagesMax;     // [2] accumulator ready
     uint64_t *tempty = tfull + 2;                // [2] accumulator drained
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint32_t *tmem_slot = &tmem_slot_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -271,6 +278,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     } else if (warp < 6) {
         // ===================================================== epilogue (TMEM lane quarter = warp % 4)
         const int q = warp & 3;
+        const int et = threadIdx.x - 64;                   // 0..127 within the epilogue warps
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
@@ -278,78 +286,130 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
             decode_tile(P, tile, pi, wb, hb, ib, nt);
             const Problem &pr = P.prob[pi];
             const int rrow = q * 32 + lane;
-            const int iw = rrow % pr.BW, ih = (rrow / pr.BW) % pr.BH, ii = rrow / (pr.BW * pr.BH);
-            const int w = wb * pr.BW + iw, h = hb * pr.BH + ih, n = ib * pr.BI + ii;
-            const bool valid = (w < pr.Wo) && (h < pr.Ho) && (n < pr.N);
-            const size_t pix = ((size_t)n * pr.Ho + h) * pr.Wo + w;
-            mbar_wait(&tfull[acc], acc_phase);
-            tcgen05_fence_after();
+            auto row_pixel = [&](int r, size_t &pix) -> bool {
+                const int iw = r & (pr.BW - 1), ih = (r >> pr.lbw) & (pr.BH - 1), ii = r >> (pr.lbw + pr.lbh);
+                const int w = wb * pr.BW + iw, h = hb * pr.BH + ih, n = ib * pr.BI + ii;
+                pix = ((size_t)n * pr.Ho + h) * pr.Wo + w;
+                return (w < pr.Wo) && (h < pr.Ho) && (n < pr.N);
+            };
+            size_t pix;
+            const bool valid = row_pixel(rrow, pix);
+            if (OUT_F32) {
+                // small fp32 outputs (head predictions, Cout <= 32): straight from registers
+                mbar_wait(&tfull[acc], acc_phase);
+                tcgen05_fence_after();
 #pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
-                const int c0 = nt * BN + ch * 32;
-                if (valid && c0 < P.Cout) {
-                    float f[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    const bool full32 = (c0 + 32 <= P.Cout);
-                    if (P.bias) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (full32 || c0 + j < P.Cout) f[j] += P.bias[c0 + j];
+                for (int ch = 0; ch < BN / 32; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
+                    const int c0 = nt * BN + ch * 32;
+                    if (valid && c0 < P.Cout) {
+                        float *op = reinterpret_cast<float *>(pr.out) + pix * P.Cout + c0;
+                        const float *rp = pr.res32 ? pr.res32 + pix * P.Cout + c0 : nullptr;
+                        for (int j = 0; j < 32; ++j) {
+                            if (c0 + j >= P.Cout) break;
+                            float f = __uint_as_float(v[j]);
+                            if (P.bias) f += P.bias[c0 + j];
+                            if (pr.res) f += __bfloat162float(pr.res[pix * P.Cout + c0 + j]);
+                            if (rp) f += rp[j];
+                            if (P.relu) f = fmaxf(f, 0.f);
+                            op[j] = f;
+                        }
                     }
-                    if (pr.res) {
-                        const __nv_bfloat16 *rp = pr.res + pix * P.Cout + c0;
-                        if (full32) {
+                }
+            } else {
+                // bf16 outputs: residual tile prefetched into shared memory with coalesced cp.async while the
+                // MMA is still running, results written back to the same staging tile, then stored coalesced
+                const bool vec_ok = (P.Cout & 7) == 0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int c = et; c < BN; c += 128) s_bias[c] = (P.bias && nt * BN + c < P.Cout) ? P.bias[nt * BN + c] : 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+                for (int half = 0; half < BN / HC; ++half) {
+                    const int cbase = nt * BN + half * HC;           // first output channel of this pass
+                    constexpr int kChunksPerRow = HC / 8;            // 16-byte chunks per staged row
+                    if (pr.res && vec_ok) {
+                        for (int c = et; c < 128 * kChunksPerRow; c += 128) {
+                            const int r = c / kChunksPerRow, k16 = c - r * kChunksPerRow;
+                            size_t rp;
+                            const bool ok = row_pixel(r, rp) && (cbase + k16 * 8 < P.Cout);
+                            const uint32_t dst = smem_u32(stage_out + (size_t)r * kPitch + k16 * 16);
+                            if (ok) {
+                                const __nv_bfloat16 *src = pr.res + rp * P.Cout + cbase + k16 * 8;
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                            }
+                        }
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                    }
+                    if (half == 0) {
+                        mbar_wait(&tfull[acc], acc_phase);
+                        tcgen05_fence_after();
+                    }
+                    if (pr.res && vec_ok) {
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                    }
+#pragma unroll 1
+                    for (int ch = 0; ch < HC / 32; ++ch) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HC + ch * 32), v);
+                        const int c0 = cbase + ch * 32;
+                        uint4 *sp = reinterpret_cast<uint4 *>(stage_out + (size_t)rrow * kPitch + ch * 64);
 #pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) {
-                                const uint4 u = *reinterpret_cast<const uint4 *>(rp + j4 * 8);
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            float f[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j4 * 8 + j]);
+                            {
+                                const float4 b0 = *reinterpret_cast<const float4 *>(&s_bias[half * HC + ch * 32 + j4 * 8]);
+                                const float4 b1 = *reinterpret_cast<const float4 *>(&s_bias[half * HC + ch * 32 + j4 * 8 + 4]);
+                                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                            }
+                            if (pr.res && !vec_ok && valid) {
+                                for (int j = 0; j < 8; ++j)
+                                    if (c0 + j4 * 8 + j < P.Cout) f[j] += __bfloat162float(pr.res[pix * P.Cout + c0 + j4 * 8 + j]);
+                            }
+                            if (pr.res && vec_ok && valid) {
+                                const uint4 u = sp[j4];
                                 const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162 *>(&uu[k]);
-                                    f[j4 * 8 + 2 * k] += __bfloat162float(b2.x);
-                                    f[j4 * 8 + 2 * k + 1] += __bfloat162float(b2.y);
+                                    const float2 r2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&uu[k]));
+                                    f[2 * k] += r2.x;
+                                    f[2 * k + 1] += r2.y;
                                 }
                             }
-                        } else {
-                            for (int j = 0; j < 32; ++j) if (c0 + j < P.Cout) f[j] += __bfloat162float(rp[j]);
-                        }
-                    }
-                    if (pr.res32) {
-                        const float *rp = pr.res32 + pix * P.Cout + c0;
-                        for (int j = 0; j < 32; ++j) if (c0 + j < P.Cout) f[j] += rp[j];
-                    }
-                    if (P.relu) {
+                            if (P.relu) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                    }
-                    if (OUT_F32) {
-                        float *op = reinterpret_cast<float *>(pr.out) + pix * P.Cout + c0;
-                        if (full32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4)
-                                *reinterpret_cast<float4 *>(op + j4 * 4) = make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
-                        } else {
-                            for (int j = 0; j < 32; ++j) if (c0 + j < P.Cout) op[j] = f[j];
-                        }
-                    } else {
-                        __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(pr.out) + pix * P.Cout + c0;
-                        if (full32) {
-#pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) {
-                                uint32_t pk[4];
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    __nv_bfloat162 b2 = __floats2bfloat162_rn(f[j4 * 8 + 2 * k], f[j4 * 8 + 2 * k + 1]);
-                                    pk[k] = *reinterpret_cast<uint32_t *>(&b2);
-                                }
-                                *reinterpret_cast<uint4 *>(op + j4 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
                             }
-                        } else {
-                            for (int j = 0; j < 32; ++j) if (c0 + j < P.Cout) op[j] = __float2bfloat16_rn(f[j]);
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                                pk[k] = *reinterpret_cast<uint32_t *>(&b2);
+                            }
+                            sp[j4] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
                     }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    // coalesced copy-out: 16 threads cover one 256-byte row segment
+                    for (int c = et; c < 128 * kChunksPerRow; c += 128) {
+                        const int r = c / kChunksPerRow, k16 = c - r * kChunksPerRow;
+                        size_t rp;
+                        if (row_pixel(r, rp) && (cbase + k16 * 8 < P.Cout)) {
+                            const uint4 u = *reinterpret_cast<const uint4 *>(stage_out + (size_t)r * kPitch + k16 * 16);
+                            __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(pr.out) + rp * P.Cout + cbase + k16 * 8;
+                            if (vec_ok) {
+                                *reinterpret_cast<uint4 *>(op) = u;
+                            } else {
+                                const __nv_bfloat16 *e8 = reinterpret_cast<const __nv_bfloat16 *>(&u);
+                                for (int j = 0; j < 8; ++j) if (cbase + k16 * 8 + j < P.Cout) op[j] = e8[j];
+                            }
+                        }
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
             }
             tcgen05_fence_before();
@@ -453,15 +513,20 @@ constexpr int kEvPool = 1024;
 thread_local cudaEvent_t g_tc_ev[kEvPool][2];
 thread_local int g_tc_ev_created = 0, g_tc_ev_used = 0;
 thread_local double g_tc_flops = 0.0;
+struct TcTrace { int nprob, N, H, W, Cin, Cout, K, stride, deform, BN, tiles, grid; double flops; };
+thread_local TcTrace g_tc_trace[kEvPool];
 
 template <int BN, bool OUT_F32, bool DEFORM>
 int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st)
 {
-    const size_t smem = 1024 + (size_t)stages * (kABytes + BN * kBK * 2) + 256;
+    constexpr int HCh = BN < 64 ? BN : 64;
+    const size_t smem = 1024 + (size_t)stages * (kABytes + BN * kBK * 2) + (OUT_F32 ? 0 : 128 * (HCh * 2 + 16));
     auto kern = conv_tc_kernel<BN, OUT_F32, DEFORM>;
     static bool attr_set = false;
     if (!attr_set) {
-        ORP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        cudaFuncAttributes fa;
+        ORP_CUDA(cudaFuncGetAttributes(&fa, kern));
+        ORP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
         attr_set = true;
     }
     int slot = -1;
@@ -477,6 +542,8 @@ int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st)
         for (int i = 0; i < P.nprob; ++i)
             fl += 2.0 * P.prob[i].N * P.prob[i].Ho * P.prob[i].Wo * (double)P.Cout * P.KH * P.KW * P.Cin;
         g_tc_flops += fl;
+        g_tc_trace[slot] = TcTrace{P.nprob, P.prob[0].N, P.prob[0].H, P.prob[0].W, P.Cin, P.Cout, P.KH, P.stride, DEFORM ? 1 : 0,
+                                   BN, P.num_tiles, grid, fl};
     }
     kern<<<grid, DEFORM ? 320 : 192, smem, st>>>(P, stages);
     ORP_LAUNCHED();
@@ -498,6 +565,12 @@ extern "C" int orp_tc_timing_collect(float *total_ms, int *launches, double *flo
         ORP_CUDA(cudaEventSynchronize(g_tc_ev[i][1]));
         ORP_CUDA(cudaEventElapsedTime(&ms, g_tc_ev[i][0], g_tc_ev[i][1]));
         sum += ms;
+        if (getenv("ORP_TC_TRACE")) {
+            const TcTrace &t = g_tc_trace[i];
+            fprintf(stderr, "tc[%3d] np=%d N=%d %4dx%-4d Cin=%4d Cout=%4d k=%d s=%d dcn=%d BN=%3d tiles=%5d grid=%3d  %8.1f us  %7.1f TFLOP/s\n",
+                    i, t.nprob, t.N, t.H, t.W, t.Cin, t.Cout, t.K, t.stride, t.deform, t.BN, t.tiles, t.grid, ms * 1e3,
+                    t.flops / (ms * 1e-3) / 1e12);
+        }
     }
     *total_ms = sum; *launches = g_tc_ev_used; *flops = g_tc_flops;
     g_tc_ev_used = 0; g_tc_flops = 0.0;
@@ -520,6 +593,15 @@ extern "C" int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const voi
 
     int BN = 256;
     if (Cout_padded % 256) BN = (Cout_padded % 128 == 0) ? 128 : (Cout_padded % 64 == 0) ? 64 : 32;
+    {
+        // narrower accumulators when the 128 x BN tiling would leave SMs idle
+        long long mtiles = 0;
+        for (int i = 0; i < nprob; ++i) {
+            const int ho = (probs[i].H + 2 * pad - (KH - 1) - 1) / stride + 1, wo = (probs[i].W + 2 * pad - (KW - 1) - 1) / stride + 1;
+            mtiles += ((long long)probs[i].N * ho * wo + 127) / 128;
+        }
+        while (BN > 64 && mtiles * (Cout_padded / BN) < 120) BN /= 2;
+    }
     TcParams P;
     memset(&P, 0, sizeof(P));
     P.nprob = nprob; P.KH = KH; P.KW = KW; P.Cin = Cin; P.cin_blocks = Cin / kBK; P.stride = stride; P.pad = pad;
@@ -537,6 +619,8 @@ extern "C" int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const voi
         if (stride * pr.BW > 256) pr.BW = 256 / stride;
         pr.BH = pow2_floor(pr.Ho < 128 / pr.BW ? pr.Ho : 128 / pr.BW);
         pr.BI = 128 / (pr.BW * pr.BH);
+        pr.lbw = 0; while ((1 << pr.lbw) < pr.BW) ++pr.lbw;
+        pr.lbh = 0; while ((1 << pr.lbh) < pr.BH) ++pr.lbh;
         pr.tiles_w = ceil_div(pr.Wo, pr.BW); pr.tiles_h = ceil_div(pr.Ho, pr.BH); pr.tiles_i = ceil_div(pr.N, pr.BI);
         pr.tile_start = mt;
         mt += pr.tiles_w * pr.tiles_h * pr.tiles_i;
@@ -575,7 +659,9 @@ extern "C" int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const voi
     }
     const int grid = P.num_tiles < sms ? P.num_tiles : sms;
     const int stage_bytes = kABytes + BN * kBK * 2;
-    int stages = (int)((227 * 1024 - 2048) / stage_bytes);
+    const int hc = BN < 64 ? BN : 64;
+    const int staging = out_f32 ? 0 : 128 * (hc * 2 + 16);
+    int stages = (int)((227 * 1024 - 4096 - 1024 - staging) / stage_bytes);
     if (stages > kStagesMax) stages = kStagesMax;
 #define ORP_TC_DISPATCH(BNV)                                                                     \
     if (BN == BNV) {                                                                             \

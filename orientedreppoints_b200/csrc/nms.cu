@@ -434,17 +434,19 @@ nms_flags_kernel(const uint8_t *__restrict__ status, const int32_t *__restrict__
     }
 }
 
-static int run_nms(const float *dets, const int32_t *segments, int n, double thr, int iou_mode,
-                   int union_mode, int order, int64_t *keep_out, int32_t *num_out, cudaStream_t st)
+// flags_out (optional): uint8 [n], 1 where the box (by ORIGINAL index) survives; when given, keep_out /
+// num_out may be NULL and the compaction is skipped (used by the fused head post-processing).
+int run_nms(const float *dets, const int32_t *segments, int n, double thr, int iou_mode, int union_mode,
+            int order, int64_t *keep_out, int32_t *num_out, cudaStream_t st, uint8_t *flags_out, bool no_sync)
 {
-    if (n < 0 || !num_out || (n > 0 && (!dets || !keep_out)))
+    if (n < 0 || (!flags_out && !num_out) || (n > 0 && (!dets || (!flags_out && !keep_out))))
         return fail(ORP_EINVAL, "orp_rnms: null pointer or negative n");
     if (iou_mode != ORP_NMS_EXACT64 && iou_mode != ORP_NMS_COMPAT32) return fail(ORP_EINVAL, "orp_rnms: bad iou_mode");
     if (union_mode < 0 || union_mode > 2) return fail(ORP_EINVAL, "orp_rnms: bad union_mode");
     int rc = ensure_device();
     if (rc) return rc;
     if (n == 0) {
-        ORP_CUDA(cudaMemsetAsync(num_out, 0, sizeof(int32_t), st));
+        if (num_out) ORP_CUDA(cudaMemsetAsync(num_out, 0, sizeof(int32_t), st));
         return ORP_OK;
     }
     Scratch S(st);
@@ -467,7 +469,7 @@ static int run_nms(const float *dets, const int32_t *segments, int n, double thr
     cub::DeviceRadixSort::SortPairs(nullptr, tb1, score_key, score_key2, iota, order_r, n, 0, 32, st);
     cub::DeviceRadixSort::SortPairs(nullptr, tb2, sweep_key, sweep_key2, iota, perm, n, 0, 64, st);
     cub::DeviceScan::ExclusiveSum(nullptr, tb3, indeg, offs, n + 1, st);
-    cub::DeviceSelect::Flagged(nullptr, tb4, vals, flags, keep_out, num_out, n, st);
+    if (keep_out && num_out) cub::DeviceSelect::Flagged(nullptr, tb4, vals, flags, keep_out, num_out, n, st);
     size_t tb = tb1 > tb2 ? tb1 : tb2;
     tb = tb > tb3 ? tb : tb3;
     tb = tb > tb4 ? tb : tb4;
@@ -528,7 +530,7 @@ static int run_nms(const float *dets, const int32_t *segments, int n, double thr
                                                                     indeg, cap, ctr);
             ORP_LAUNCHED();
         }
-        if (cap >= all_pairs) break;   // cannot overflow
+        if (cap >= all_pairs || no_sync) break;   // cannot overflow / caller forbids the host round trip
         // overflow check needs the host; it is the only sync of the call and only happens when
         // the edge list could in principle exceed its capacity
         NmsCounters h;
@@ -571,10 +573,14 @@ static int run_nms(const float *dets, const int32_t *segments, int n, double thr
         ORP_CUDA(cudaLaunchCooperativeKernel((void *)nms_resolve_kernel, dim3(grid), dim3(256), args, 0, st));
         ORP_LAUNCHED();
     }
-    nms_flags_kernel<<<G, T, 0, st>>>(status, order_r, rank, n, order, flags, vals);
+    nms_flags_kernel<<<G, T, 0, st>>>(status, order_r, rank, n, flags_out ? ORP_ORDER_INDEX_ASC : order,
+                                      flags_out ? flags_out : flags, vals);
     ORP_LAUNCHED();
-    ORP_CUDA(cub::DeviceSelect::Flagged(tmp, tb4, vals, flags, keep_out, num_out, n, st));
-    count_launches(3);
+    if (keep_out && num_out) {
+        if (flags_out && order != ORP_ORDER_INDEX_ASC) return fail(ORP_EINVAL, "orp_rnms: flags_out needs index order");
+        ORP_CUDA(cub::DeviceSelect::Flagged(tmp, tb4, vals, flags_out ? flags_out : flags, keep_out, num_out, n, st));
+        count_launches(3);
+    }
 
     // stash the counters for orp_rnms_last_stats (async copy into pinned memory)
     if (!g_stats_pinned) ORP_CUDA(cudaHostAlloc(&g_stats_pinned, sizeof(NmsCounters), cudaHostAllocDefault));
@@ -589,7 +595,7 @@ extern "C" int orp_rnms(const float *dets, const int32_t *segments, int n, doubl
                         int union_mode, int order, int64_t *keep_out, int32_t *num_out, void *stream)
 {
     return orp::run_nms(dets, segments, n, iou_thr, iou_mode, union_mode, order, keep_out, num_out,
-                        static_cast<cudaStream_t>(stream));
+                        static_cast<cudaStream_t>(stream), nullptr, false);
 }
 
 extern "C" int orp_rnms_last_sweep_ms(float *ms)
@@ -641,7 +647,7 @@ extern "C" int orp_poly_nms_host(int *keep_out, int *num_out, const float *polys
         // the caller sorted by score already (poly_nms.pyx:19-21); our stable descending sort
         // reproduces that order exactly, so SCORE_DESC output == positions in the sorted input
         rc = run_nms(d, nullptr, polys_num, (double)nms_overlap_thresh, ORP_NMS_EXACT64, ORP_UNION_GUARD,
-                     ORP_ORDER_SCORE_DESC, k, cnt, st);
+                     ORP_ORDER_SCORE_DESC, k, cnt, st, nullptr, false);
         if (rc) break;
         int32_t hc = 0;
         if (cudaMemcpyAsync(&hc, cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||

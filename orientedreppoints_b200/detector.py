@@ -216,14 +216,51 @@ class OrientedRepPointsDetector:
         feats = self.extract_feat(img)
         return self.head(feats), feats
 
+    # ------------------------------------------------------------------ CUDA graph of the dense graph
+    def capture(self, img_shape):
+        """Capture backbone + FPN + head for a fixed input shape into ONE CUDA graph (static buffers): the
+        ~180 kernel launches of a step become a single graph launch, which removes the host-side launch
+        cost that otherwise dominates a one-tile step.  simple_test() replays it when the shape matches."""
+        shape = tuple(img_shape)
+        self._g_img = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):                                      # warm-up: lazy weight prep, func attributes
+                self.forward_dense(self._g_img)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._g_out = self.forward_dense(self._g_img)
+        self._g_shape = shape
+        return self
+
+    def forward_dense_graph(self, img):
+        self._g_img.copy_(img, non_blocking=True)
+        self._graph.replay()
+        return self._g_out
+
     # ------------------------------------------------------------------ simple_test
     def simple_test(self, img, img_metas=None, rescale=True, return_tensors=False):
         from .core.get_bboxes import get_bboxes
-        outs, _ = self.forward_dense(img)
+        if getattr(self, "_g_shape", None) == tuple(img.shape):
+            outs, _ = self.forward_dense_graph(img)
+        else:
+            outs, _ = self.forward_dense(img)
         n = img.shape[0]
         if img_metas is None:
             img_metas = [dict(scale_factor=1.0) for _ in range(n)]
-        results = get_bboxes([o[0] for o in outs], [o[2] for o in outs], STRIDES, img_metas, self.test_cfg, rescale)
+        if getattr(self, "fused_post", True):
+            from .core.get_bboxes import get_bboxes_fused
+            dets, labels, counts = get_bboxes_fused([o[0] for o in outs], [o[2] for o in outs], STRIDES, img_metas,
+                                                    self.test_cfg, rescale)
+            if return_tensors == "padded":
+                return dets, labels, counts
+            cnt = counts.tolist()                                      # the one host sync of a step
+            results = [(dets[i, :cnt[i]], labels[i, :cnt[i]]) for i in range(n)]
+        else:
+            results = get_bboxes([o[0] for o in outs], [o[2] for o in outs], STRIDES, img_metas, self.test_cfg, rescale)
         if return_tensors:
             return results
         from .core.transforms import rbbox2result

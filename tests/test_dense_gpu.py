@@ -168,3 +168,32 @@ def test_dense_graph_bf16_vs_f32_engine(cuda, sd):
             a, b = o16[lvl][k], o32[lvl][k]
             assert a.shape == b.shape and a.dtype == torch.float32
             assert float((a - b).abs().max()) < 0.08 * max(1.0, float(b.abs().max())), (lvl, k)
+
+
+def test_fused_postprocess_equals_torch_mirror_and_oracle(cuda, sd):
+    """orp_head_postprocess (one device pipeline) == the op-by-op mirror of get_bboxes/multiclass_rnms ==
+    the restated reference pipeline on the CPU oracle: labels/order bit-exact, scores bit-exact, coordinates 1e-3 px"""
+    from oracle import torch_reference as tr
+    from orientedreppoints_b200.core.get_bboxes import get_bboxes, get_bboxes_fused
+    from orientedreppoints_b200.detector import OrientedRepPointsDetector, STRIDES
+    for thr, size, cap in ((0.02, 256, 2000), (0.0, 384, 300), (0.5, 256, 2000)):
+        det = OrientedRepPointsDetector(sd, 50, cuda, "fp32", test_cfg=dict(score_thr=thr, max_per_img=cap))
+        img = torch.randn(2, 3, size, size, generator=torch.Generator().manual_seed(5)).to(cuda)
+        outs, _ = det.forward_dense(img)
+        cls, ref = [o[0] for o in outs], [o[2] for o in outs]
+        metas = [dict(scale_factor=1.0), dict(scale_factor=1.0)]
+        mirror = get_bboxes(cls, ref, STRIDES, metas, det.test_cfg, rescale=True)
+        dets, labels, counts = get_bboxes_fused(cls, ref, STRIDES, metas, det.test_cfg, rescale=True)
+        counts = counts.tolist()
+        for i in range(2):
+            d, l = dets[i, :counts[i]], labels[i, :counts[i]]
+            md, ml = mirror[i]
+            assert d.shape == md.shape, (thr, i, d.shape, md.shape)
+            assert torch.equal(l, ml)
+            assert torch.equal(d[:, -1], md[:, -1])
+            assert float((d - md).abs().max()) < 1e-3 if d.numel() else True
+            assert bool((labels[i, counts[i]:] == -1).all())
+        if thr == 0.02:
+            rd, rl = tr.get_bboxes_single([c[0].permute(2, 0, 1) for c in cls], [r[0].permute(2, 0, 1).cpu() for r in ref],
+                                          score_thr=thr, max_per_img=cap)
+            assert torch.equal(labels[0, :counts[0]].cpu(), rl) and torch.equal(dets[0, :counts[0], -1].cpu(), rd[:, -1])

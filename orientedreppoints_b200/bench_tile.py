@@ -60,32 +60,19 @@ def run(args, rank, world, local, benchmod):
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     warm = max(args.warmup, 3)
 
-    def step_device():
-        return det.simple_test(img, return_tensors=True)
+    from . import gather as G
 
-    def gather(results):
-        """fixed-layout detection buffer [batch, 2000, 28] (27 + label) + counts, ONE all_gather"""
-        buf = torch.zeros((batch, 2000, 28), dtype=torch.float32, device=dev)
-        cnt = torch.zeros((batch,), dtype=torch.int32, device=dev)
-        for i, (d, l) in enumerate(results):
-            k = d.shape[0]
-            buf[i, :k, :27] = d
-            buf[i, :k, 27] = l.float()
-            cnt[i] = k
-        if world > 1:
-            import torch.distributed as dist
-            allb = torch.empty((world,) + tuple(buf.shape), dtype=buf.dtype, device=dev)
-            allc = torch.empty((world, batch), dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(allb, buf)
-            dist.all_gather_into_tensor(allc, cnt)
-            return allb, allc
-        return buf, cnt
+    def step_device():
+        """one step, device resident: dense graph -> fused post-processing -> packed detections -> all-gather"""
+        dets, labels, counts = det.simple_test(img, return_tensors="padded")
+        buf, cnt = G.pack(dets, labels, counts)
+        return G.all_gather_detections(buf, cnt)
 
     use_graph = not getattr(args, "no_graph", False)
     if use_graph:
         det.capture(img.shape)
     for _ in range(warm):
-        gather(step_device())
+        step_device()
     benchmod.barrier(world)
     sampler = benchmod.ClockSampler(local)
     if rank == 0:
@@ -96,8 +83,7 @@ def run(args, rank, world, local, benchmod):
     for s in range(args.steps):
         flush.fill_(s & 0xFF)
         ev[s][0].record()
-        res = step_device()
-        gather(res)
+        all_buf, all_cnt = step_device()
         ev[s][1].record()
     benchmod.barrier(world)
     launches = _lib.launch_count()
@@ -124,14 +110,15 @@ def run(args, rank, world, local, benchmod):
             launches += (launches_dense - launches) // 1 * 0 + args.steps * ((launches_dense - launches))
     total_ms = benchmod.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), world)
     ms_step = total_ms / args.steps
-    ndet = [int(r[0].shape[0]) for r in res]
+    ndet = [int(v) for v in all_cnt.reshape(-1).tolist()]
 
     # end to end through the public API: pinned host tiles -> H2D -> simple_test -> rbbox2result (D2H)
     def step_e2e():
         x = img_host.to(dev, non_blocking=True)
-        r = det.simple_test(x, return_tensors=True)
-        gather(r)
-        return [rbbox2result(d, l, 16) for d, l in r]
+        dets, labels, counts = det.simple_test(x, return_tensors="padded")
+        G.all_gather_detections(*G.pack(dets, labels, counts))
+        cnt = counts.tolist()                                         # device -> host: the step's result
+        return [rbbox2result(dets[i, :cnt[i]], labels[i, :cnt[i]], 16) for i in range(batch)]
 
     for _ in range(2):
         step_e2e()

@@ -18,7 +18,7 @@
 //   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns), bias / residual / ReLU, bf16 or fp32 NHWC
 //               stores.  TMEM holds two accumulators so the epilogue of tile i overlaps the main loop
 //               of tile i+1.
-//   warps 6-9   (deformable variant only) A-operand producers: per output pixel and tap the 4-corner
+//   warps 6-13  (deformable variant only) A-operand producers: per output pixel and tap the 4-corner
 //               bilinear sample of the reference (deform_conv_cuda_kernel.cu:84-115) is computed in
 //               fp32 from bf16 features and written to shared memory in the same swizzled layout.
 // Several "problems" (the five FPN levels, which share the head weights) are served by ONE launch.
@@ -178,7 +178,7 @@ __device__ __forceinline__ void decode_tile(const TcParams &P, int tile, int &pi
 // BN: accumulator width (32..256).  OUT_F32: fp32 output (head predictions) instead of bf16.
 // DEFORM: A operand produced by warps 6-9 (bilinear gather) instead of TMA.
 template <int BN, bool OUT_F32, bool DEFORM>
-__global__ void __launch_bounds__(DEFORM ? 320 : 192, 1)
+__global__ void __launch_bounds__(DEFORM ? 448 : 192, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -210,7 +210,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     if (warp == 1) {
         if (elect_one()) {
             for (int s = 0; s < stages; ++s) {
-                mbar_init(&full[s], DEFORM ? 1 + 128 : 1);
+                mbar_init(&full[s], DEFORM ? 1 + 256 : 1);
                 mbar_init(&empty[s], 1);
             }
             for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
@@ -418,46 +418,74 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (DEFORM) {
-        // ===================================================== deformable A-operand producers (warps 6-9)
-        const int rrow = (warp - 6) * 32 + lane;          // one output pixel (= one smem row) per thread
+        // ===================================================== deformable A-operand producers (warps 6-13)
+        // Per tap: threads 0-127 compute the bilinear parameters of their output pixel (4 weights + 4 element
+        // offsets, deform_conv_cuda_kernel.cu:84-115 + the validity test of :229) into a shared table; then all
+        // 256 threads gather: 8 consecutive lanes fetch the 8 x 16 B of one pixel's 64-channel block for each of
+        // the 4 corners (every load instruction covers whole 128-byte lines), blend in fp32, round to bf16 and
+        // store to the stage in the 128-byte-swizzled K-major layout the MMA expects.
+        __shared__ float4 s_w[2][128];
+        __shared__ int4 s_o[2][128];
+        const int pt = threadIdx.x - 192;                  // 0..255
         Ring r(stages);
+        int tb = 0;
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
             int pi, wb, hb, ib, nt;
             decode_tile(P, tile, pi, wb, hb, ib, nt);
             const Problem &pr = P.prob[pi];
-            const int iw = rrow % pr.BW, ih = (rrow / pr.BW) % pr.BH, ii = rrow / (pr.BW * pr.BH);
-            const int w = wb * pr.BW + iw, h = hb * pr.BH + ih, n = ib * pr.BI + ii;
-            const bool valid = (w < pr.Wo) && (h < pr.Ho) && (n < pr.N);
-            const __nv_bfloat16 *img = pr.x + (size_t)(valid ? n : 0) * pr.H * pr.W * P.Cin;
+            bool valid = false;
+            int w = 0, h = 0, n = 0;
+            if (pt < 128) {
+                const int iw = pt & (pr.BW - 1), ih = (pt >> pr.lbw) & (pr.BH - 1), ii = pt >> (pr.lbw + pr.lbh);
+                w = wb * pr.BW + iw; h = hb * pr.BH + ih; n = ib * pr.BI + ii;
+                valid = (w < pr.Wo) && (h < pr.Ho) && (n < pr.N);
+            }
             const float *offp = pr.offset + (((size_t)(valid ? n : 0) * pr.Ho + (valid ? h : 0)) * pr.Wo + (valid ? w : 0)) * (2 * P.KH * P.KW);
+            const int img0 = (valid ? n : 0) * pr.H * pr.W * P.Cin;
             for (int tap = 0; tap < P.KH * P.KW; ++tap) {
-                const int kh = tap / P.KW, kw = tap - kh * P.KW;
-                // deformable_im2col_gpu_kernel (deform_conv_cuda_kernel.cu:216-237)
-                float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
-                const __nv_bfloat16 *p1 = img, *p2 = img, *p3 = img, *p4 = img;
-                if (valid) {
-                    const float h_im = (float)(h * P.stride - P.pad + kh) + offp[2 * tap];
-                    const float w_im = (float)(w * P.stride - P.pad + kw) + offp[2 * tap + 1];
-                    if (h_im > -1.f && w_im > -1.f && h_im < (float)pr.H && w_im < (float)pr.W) {
-                        const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-                        const int h_high = h_low + 1, w_high = w_low + 1;
-                        const float lh = h_im - (float)h_low, lw = w_im - (float)w_low, hh = 1.f - lh, hw = 1.f - lw;
-                        if (h_low >= 0 && w_low >= 0) { w1 = hh * hw; p1 = img + ((size_t)h_low * pr.W + w_low) * P.Cin; }
-                        if (h_low >= 0 && w_high <= pr.W - 1) { w2 = hh * lw; p2 = img + ((size_t)h_low * pr.W + w_high) * P.Cin; }
-                        if (h_high <= pr.H - 1 && w_low >= 0) { w3 = lh * hw; p3 = img + ((size_t)h_high * pr.W + w_low) * P.Cin; }
-                        if (h_high <= pr.H - 1 && w_high <= pr.W - 1) { w4 = lh * lw; p4 = img + ((size_t)h_high * pr.W + w_high) * P.Cin; }
+                if (pt < 128) {
+                    const int kh = tap / P.KW, kw = tap - kh * P.KW;
+                    float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    int4 ov = make_int4(img0, img0, img0, img0);
+                    if (valid) {
+                        const float h_im = (float)(h * P.stride - P.pad + kh) + offp[2 * tap];
+                        const float w_im = (float)(w * P.stride - P.pad + kw) + offp[2 * tap + 1];
+                        if (h_im > -1.f && w_im > -1.f && h_im < (float)pr.H && w_im < (float)pr.W) {
+                            const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                            const int h_high = h_low + 1, w_high = w_low + 1;
+                            const float lh = h_im - (float)h_low, lw = w_im - (float)w_low, hh = 1.f - lh, hw = 1.f - lw;
+                            if (h_low >= 0 && w_low >= 0) { wv.x = hh * hw; ov.x = img0 + (h_low * pr.W + w_low) * P.Cin; }
+                            if (h_low >= 0 && w_high <= pr.W - 1) { wv.y = hh * lw; ov.y = img0 + (h_low * pr.W + w_high) * P.Cin; }
+                            if (h_high <= pr.H - 1 && w_low >= 0) { wv.z = lh * hw; ov.z = img0 + (h_high * pr.W + w_low) * P.Cin; }
+                            if (h_high <= pr.H - 1 && w_high <= pr.W - 1) { wv.w = lh * lw; ov.w = img0 + (h_high * pr.W + w_high) * P.Cin; }
+                        }
                     }
+                    s_w[tb][pt] = wv;
+                    s_o[tb][pt] = ov;
                 }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
                 for (int cb = 0; cb < P.cin_blocks; ++cb) {
                     mbar_wait(&empty[r.stage], r.phase ^ 1);
-                    uint8_t *sa = smem + (size_t)r.stage * kStageBytes + (size_t)rrow * 128;
+                    uint8_t *sa = smem + (size_t)r.stage * kStageBytes;
+                    uint4 u[4][4];
 #pragma unroll
-                    for (int c16 = 0; c16 < 8; ++c16) {
+                    for (int it = 0; it < 4; ++it) {
+                        const int item = pt + it * 256, row = item >> 3, c16 = item & 7;
+                        const int4 ov = s_o[tb][row];
                         const int co = cb * kBK + c16 * 8;
-                        const uint4 u1 = *reinterpret_cast<const uint4 *>(p1 + co), u2 = *reinterpret_cast<const uint4 *>(p2 + co);
-                        const uint4 u3 = *reinterpret_cast<const uint4 *>(p3 + co), u4 = *reinterpret_cast<const uint4 *>(p4 + co);
-                        const uint32_t a1[4] = {u1.x, u1.y, u1.z, u1.w}, a2[4] = {u2.x, u2.y, u2.z, u2.w};
-                        const uint32_t a3[4] = {u3.x, u3.y, u3.z, u3.w}, a4[4] = {u4.x, u4.y, u4.z, u4.w};
+                        u[it][0] = *reinterpret_cast<const uint4 *>(pr.x + ov.x + co);
+                        u[it][1] = *reinterpret_cast<const uint4 *>(pr.x + ov.y + co);
+                        u[it][2] = *reinterpret_cast<const uint4 *>(pr.x + ov.z + co);
+                        u[it][3] = *reinterpret_cast<const uint4 *>(pr.x + ov.w + co);
+                    }
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int item = pt + it * 256, row = item >> 3, c16 = item & 7;
+                        const float4 wv = s_w[tb][row];
+                        const uint32_t *a1 = reinterpret_cast<const uint32_t *>(&u[it][0]);
+                        const uint32_t *a2 = reinterpret_cast<const uint32_t *>(&u[it][1]);
+                        const uint32_t *a3 = reinterpret_cast<const uint32_t *>(&u[it][2]);
+                        const uint32_t *a4 = reinterpret_cast<const uint32_t *>(&u[it][3]);
                         uint32_t pk[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -465,18 +493,18 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a2[k]));
                             const float2 f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a3[k]));
                             const float2 f4 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a4[k]));
-                            const float vx = w1 * f1.x + w2 * f2.x + w3 * f3.x + w4 * f4.x;
-                            const float vy = w1 * f1.y + w2 * f2.y + w3 * f3.y + w4 * f4.y;
+                            const float vx = wv.x * f1.x + wv.y * f2.x + wv.z * f3.x + wv.w * f4.x;
+                            const float vy = wv.x * f1.y + wv.y * f2.y + wv.z * f3.y + wv.w * f4.y;
                             __nv_bfloat162 b2 = __floats2bfloat162_rn(vx, vy);
                             pk[k] = *reinterpret_cast<uint32_t *>(&b2);
                         }
-                        // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
-                        *reinterpret_cast<uint4 *>(sa + ((c16 ^ (rrow & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4 *>(sa + (size_t)row * 128 + ((c16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy (UMMA reads smem)
                     mbar_arrive(&full[r.stage]);
                     r.next();
                 }
+                tb ^= 1;
             }
         }
     }
@@ -545,7 +573,7 @@ int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st)
         g_tc_trace[slot] = TcTrace{P.nprob, P.prob[0].N, P.prob[0].H, P.prob[0].W, P.Cin, P.Cout, P.KH, P.stride, DEFORM ? 1 : 0,
                                    BN, P.num_tiles, grid, fl};
     }
-    kern<<<grid, DEFORM ? 320 : 192, smem, st>>>(P, stages);
+    kern<<<grid, DEFORM ? 448 : 192, smem, st>>>(P, stages);
     ORP_LAUNCHED();
     if (slot >= 0) ORP_CUDA(cudaEventRecord(g_tc_ev[slot][1], st));
     return ORP_OK;
@@ -663,6 +691,7 @@ extern "C" int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const voi
     const int staging = out_f32 ? 0 : 128 * (hc * 2 + 16);
     int stages = (int)((227 * 1024 - 4096 - 1024 - staging) / stage_bytes);
     if (stages > kStagesMax) stages = kStagesMax;
+    if (deform && stages > 3) stages = 3;     // leave L1 capacity for the bilinear gather (corner reuse between neighbouring pixels)
 #define ORP_TC_DISPATCH(BNV)                                                                     \
     if (BN == BNV) {                                                                             \
         if (deform) return out_f32 ? launch_tc<BNV, true, true>(P, stages, grid, st) : launch_tc<BNV, false, true>(P, stages, grid, st); \

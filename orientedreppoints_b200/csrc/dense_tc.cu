@@ -55,7 +55,10 @@ struct Problem {
 struct alignas(64) TcParams {
     CUtensorMap tmA[kMaxProb];
     CUtensorMap tmB;
+    CUtensorMap tmOut[kMaxProb];              // bf16 output tensors, box {64 ch, BW, BH, BI} (TMA-store epilogue)
+    CUtensorMap tmRes[kMaxProb];              // bf16 residual tensors, same boxes
     Problem prob[kMaxProb];
+    int tma_epi, epi_bufs;                    // TMA epilogue on/off; output staging buffers (1 or 2)
     int nprob, num_m_tiles, n_tiles_n, num_tiles;
     int KH, KW, Cin, cin_blocks, stride, pad, Cout, relu;
     const float *bias;
@@ -191,6 +194,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     uint8_t *stage_out = smem + (size_t)stages * kStageBytes;
     __shared__ uint64_t bars[2 * kStagesMax + 4];
     __shared__ float s_bias[256];
+    __shared__ uint64_t res_bar[2];              // residual tile landed (TMA epilogue)
     __shared__ uint32_t tmem_slot_s;
     uint64_t *full = bars;                       // [stages]  TMA bytes landed (+ producer arrivals when DEFORM)
     uint64_t *empty = bars + kStagesMax;         // [stages]  MMA finished reading the stage
@@ -213,7 +217,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 mbar_init(&full[s], DEFORM ? 1 + 256 : 1);
                 mbar_init(&empty[s], 1);
             }
-            for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+            for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); mbar_init(&res_bar[a], 1); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -279,6 +283,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
         // ===================================================== epilogue (TMEM lane quarter = warp % 4)
         const int q = warp & 3;
         const int et = threadIdx.x - 64;                   // 0..127 within the epilogue warps
+        int tma_g = 0;                                     // passes issued so far through the TMA epilogue
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
@@ -315,6 +320,98 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             if (P.relu) f = fmaxf(f, 0.f);
                             op[j] = f;
                         }
+                    }
+                }
+            } else if (P.tma_epi) {
+                // bf16 outputs through the TMA unit: 64-channel passes; the residual pass tile is prefetched by
+                // TMA (128-byte swizzle) one pass ahead, results are written to a swizzled staging tile and
+                // stored with cp.async.bulk.tensor (coalescing and partial-tile clipping done by hardware)
+                uint8_t *Obuf = stage_out;                               // [epi_bufs][16 KiB]
+                uint8_t *Rbuf = stage_out + (size_t)P.epi_bufs * 16384;  // [2][16 KiB]
+                const bool io = (et == 0);
+                constexpr int kPasses = BN / 64;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int c = et; c < BN; c += 128) s_bias[c] = (P.bias && nt * BN + c < P.Cout) ? P.bias[nt * BN + c] : 0.f;
+                if (io && pr.res && tma_g == 0) {                         // prologue: residual of the very first pass
+                    mbar_expect_tx(&res_bar[0], 16384);
+                    tma_load_4d(Rbuf, &P.tmRes[pi], &res_bar[0], nt * BN, wb * pr.BW, hb * pr.BH, ib * pr.BI);
+                }
+#pragma unroll 1
+                for (int half = 0; half < kPasses; ++half, ++tma_g) {
+                    const int ob = tma_g % P.epi_bufs, rb = tma_g & 1;
+                    if (io) {
+                        if (P.epi_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        // prefetch the residual of the NEXT pass (possibly of the next tile) into the other buffer
+                        int npi = pi, nwb = wb, nhb = hb, nib = ib, nnt = nt, nhalf = half + 1;
+                        bool have_next = true;
+                        if (nhalf == kPasses) {
+                            nhalf = 0;
+                            const int ntile = tile + gridDim.x;
+                            have_next = ntile < P.num_tiles;
+                            if (have_next) decode_tile(P, ntile, npi, nwb, nhb, nib, nnt);
+                        }
+                        if (have_next && P.prob[npi].res) {
+                            const Problem &np = P.prob[npi];
+                            mbar_expect_tx(&res_bar[rb ^ 1], 16384);
+                            tma_load_4d(Rbuf + (size_t)(rb ^ 1) * 16384, &P.tmRes[npi], &res_bar[rb ^ 1], nnt * BN + nhalf * 64,
+                                        nwb * np.BW, nhb * np.BH, nib * np.BI);
+                        }
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");       // staging buffer `ob` is free, bias staged
+                    if (half == 0) {
+                        mbar_wait(&tfull[acc], acc_phase);
+                        tcgen05_fence_after();
+                    }
+                    if (pr.res) mbar_wait(&res_bar[rb], (uint32_t)((tma_g >> 1) & 1));
+                    uint8_t *orow = Obuf + (size_t)ob * 16384 + (size_t)rrow * 128;
+                    const uint8_t *rrow_p = Rbuf + (size_t)rb * 16384 + (size_t)rrow * 128;
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * 64 + ch * 32), v);
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const int c16 = ch * 4 + j4;                  // 16-byte chunk inside the 128-byte row
+                            const int sw = (c16 ^ (rrow & 7)) << 4;
+                            float f[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j4 * 8 + j]);
+                            const float4 b0 = *reinterpret_cast<const float4 *>(&s_bias[half * 64 + c16 * 8]);
+                            const float4 b1 = *reinterpret_cast<const float4 *>(&s_bias[half * 64 + c16 * 8 + 4]);
+                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                            if (pr.res) {
+                                const uint4 u = *reinterpret_cast<const uint4 *>(rrow_p + sw);
+                                const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const float2 r2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&uu[k]));
+                                    f[2 * k] += r2.x;
+                                    f[2 * k + 1] += r2.y;
+                                }
+                            }
+                            if (P.relu) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                            }
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                                pk[k] = *reinterpret_cast<uint32_t *>(&b2);
+                            }
+                            *reinterpret_cast<uint4 *>(orow + sw) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync 3, 128;" ::: "memory");       // staging written by all, residual buffer consumed by all
+                    if (io) {
+                        asm volatile(
+                            "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                            ::"l"(&P.tmOut[pi]), "r"(smem_u32(Obuf + (size_t)ob * 16384)), "r"(nt * BN + half * 64),
+                              "r"(wb * pr.BW), "r"(hb * pr.BH), "r"(ib * pr.BI) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
             } else {
@@ -417,6 +514,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
             if (lane == 0) mbar_arrive(&tempty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (P.tma_epi && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores drained before exit
     } else if (DEFORM) {
         // ===================================================== deformable A-operand producers (warps 6-13)
         // Per tap: threads 0-127 compute the bilinear parameters of their output pixel (4 weights + 4 element
@@ -545,10 +643,9 @@ struct TcTrace { int nprob, N, H, W, Cin, Cout, K, stride, deform, BN, tiles, gr
 thread_local TcTrace g_tc_trace[kEvPool];
 
 template <int BN, bool OUT_F32, bool DEFORM>
-int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st)
+int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st, int staging_bytes)
 {
-    constexpr int HCh = BN < 64 ? BN : 64;
-    const size_t smem = 1024 + (size_t)stages * (kABytes + BN * kBK * 2) + (OUT_F32 ? 0 : 128 * (HCh * 2 + 16));
+    const size_t smem = 1024 + (size_t)stages * (kABytes + BN * kBK * 2) + (size_t)staging_bytes;
     auto kern = conv_tc_kernel<BN, OUT_F32, DEFORM>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -679,6 +776,32 @@ extern "C" int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const voi
     }
     P.num_m_tiles = mt;
     P.num_tiles = mt * P.n_tiles_n;
+    // TMA epilogue: bf16 outputs whose channel count is a multiple of 64
+    bool any_res = false;
+    for (int i = 0; i < nprob; ++i) any_res = any_res || (probs[i].residual_bf16 != nullptr);
+    P.tma_epi = (!out_f32 && (Cout % 64 == 0) && BN >= 64) ? 1 : 0;
+    if (getenv("ORP_TC_NO_TMA_EPI")) P.tma_epi = 0;
+    const bool mem_bound = any_res || (KH * KW * (Cin / kBK) <= 8);
+    P.epi_bufs = mem_bound ? 2 : 1;
+    if (P.tma_epi) {
+        for (int i = 0; i < nprob; ++i) {
+            const Problem &pr = P.prob[i];
+            cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)pr.Wo, (cuuint64_t)pr.Ho, (cuuint64_t)pr.N};
+            cuuint64_t gstr[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)pr.Wo * Cout * 2, (cuuint64_t)pr.Ho * pr.Wo * Cout * 2};
+            cuuint32_t box[4] = {64u, (cuuint32_t)pr.BW, (cuuint32_t)pr.BH, (cuuint32_t)pr.BI};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult r = enc(&P.tmOut[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, pr.out, gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_bf16: cuTensorMapEncodeTiled(out) failed");
+            if (pr.res) {
+                r = enc(&P.tmRes[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16 *>(pr.res), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_bf16: cuTensorMapEncodeTiled(residual) failed");
+            }
+        }
+    }
     int sms = 148;
     {
         int dev = 0;
@@ -688,14 +811,15 @@ extern "C" int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const voi
     const int grid = P.num_tiles < sms ? P.num_tiles : sms;
     const int stage_bytes = kABytes + BN * kBK * 2;
     const int hc = BN < 64 ? BN : 64;
-    const int staging = out_f32 ? 0 : 128 * (hc * 2 + 16);
+    int staging = out_f32 ? 0 : 128 * (hc * 2 + 16);
+    if (P.tma_epi) staging = (P.epi_bufs + (any_res ? 2 : 0)) * 16384;
     int stages = (int)((227 * 1024 - 4096 - 1024 - staging) / stage_bytes);
     if (stages > kStagesMax) stages = kStagesMax;
     if (deform && stages > 3) stages = 3;     // leave L1 capacity for the bilinear gather (corner reuse between neighbouring pixels)
 #define ORP_TC_DISPATCH(BNV)                                                                     \
     if (BN == BNV) {                                                                             \
-        if (deform) return out_f32 ? launch_tc<BNV, true, true>(P, stages, grid, st) : launch_tc<BNV, false, true>(P, stages, grid, st); \
-        return out_f32 ? launch_tc<BNV, true, false>(P, stages, grid, st) : launch_tc<BNV, false, false>(P, stages, grid, st);          \
+        if (deform) return out_f32 ? launch_tc<BNV, true, true>(P, stages, grid, st, staging) : launch_tc<BNV, false, true>(P, stages, grid, st, staging); \
+        return out_f32 ? launch_tc<BNV, true, false>(P, stages, grid, st, staging) : launch_tc<BNV, false, false>(P, stages, grid, st, staging);          \
     }
     ORP_TC_DISPATCH(256)
     ORP_TC_DISPATCH(128)

@@ -203,3 +203,34 @@ def test_box_iou_rotated_known_answers(cuda):
     b2 = torch.tensor([[1, 1, 1, 1, 0], [.5, .5, 1, 1, np.pi / 4]], device=cuda)
     out = box_iou_rotated(b1, b2).cpu().numpy()
     assert np.allclose(out, [[1 / 7, 0.70710678]], atol=1e-5)                 # SURVEY section 0 probe values
+
+
+# ------------------------------------------------------------------------------- ResultMerge
+def test_result_merge_gpu_vs_restated_reference(cuda, po, tmp_path):
+    from orientedreppoints_b200.dota import result_merge as rm
+    rng = np.random.RandomState(0)
+    lines = []
+    for img in ("P0007", "P0003", "P0011"):
+        for (tx, ty) in ((0, 0), (824, 0), (0, 824), (824, 824)):
+            d = po.gen_rotated_boxes(120, seed=rng.randint(1 << 30), extent=1024.0)
+            for r in d:
+                lines.append("%s__1__%d___%d %s %s\n" % (img, tx, ty, repr(float(r[8])), " ".join("%.1f" % v for v in r[:8])))
+    rng.shuffle(lines)
+    # restated mergesingle + nmsbynamedict over the CPU oracle (fp64 IoU on the float32 coordinates the GPU sees)
+    names, ids, dets = rm.parse_result_lines(lines)
+    exp = []
+    for k, name in enumerate(names):
+        idx = np.nonzero(ids == k)[0]
+        keep = po.nms_poly_f64(dets[idx].astype(np.float32), 0.1, fast=True)
+        for i in idx[keep]:
+            exp.append(name + ' ' + str(float(dets[i, 8])) + ' ' + ' '.join(map(str, [float(v) for v in dets[i, :8]])))
+    got = rm.merge_lines(lines)
+    assert got == exp and len(got) > 300
+    src = tmp_path / "raw"; dst = tmp_path / "merged"
+    src.mkdir()
+    (src / "Task1_plane.txt").write_text("".join(lines))
+    rm.mergebypoly(str(src), str(dst))
+    assert (dst / "Task1_plane.txt").read_text().splitlines() == exp
+    assert rm.py_cpu_nms_poly(np.zeros((0, 9)), 0.1) == []
+    d = po.gen_rotated_boxes(500, seed=3)
+    assert rm.py_cpu_nms_poly(d.astype(np.float64), 0.3) == [int(i) for i in po.nms_poly_f64(d, 0.3)]

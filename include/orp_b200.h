@@ -245,7 +245,13 @@ int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const void *w, int C
                     int KH, int KW, int Cin, int stride, int pad, const float *bias, int relu, int out_f32,
                     int deform, void *stream);
 
-/* conv1 of the ResNet stem as a GEMM: NCHW fp32 image -> bf16 [N,Ho,Wo,192] rows
+/* conv1 of the ResNet stem (7x7, stride 2, pad 3, 3 channels; resnet.py:495) + folded BN + ReLU straight
+ * from the NCHW fp32 image: the im2col rows (k = (kh*7+kw)*3 + c, K padded 147 -> 192) are built in shared
+ * memory by producer warps, never in HBM.  w192: bf16 [64][192]; out: bf16 NHWC [N, H/2, W/2, 64]. */
+int orp_stem_conv_bf16(const float *img_nchw, int N, int H, int W, const void *w192, const float *bias, int relu,
+                       void *out, void *stream);
+/* the same im2col rows materialised (kept for tests / comparison):
+ * conv1 of the ResNet stem as a GEMM: NCHW fp32 image -> bf16 [N,Ho,Wo,192] rows
  * (k = (kh*7+kw)*3 + c, zero above 147) */
 int orp_stem_im2col_bf16(const float *img_nchw, int N, int H, int W, void *out, void *stream);
 int orp_maxpool3x3s2_bf16(const void *x, int N, int H, int W, int C, void *y, void *stream);

@@ -59,6 +59,7 @@ struct alignas(64) TcParams {
     CUtensorMap tmRes[kMaxProb];              // bf16 residual tensors, same boxes
     Problem prob[kMaxProb];
     int tma_epi, epi_bufs;                    // TMA epilogue on/off; output staging buffers (1 or 2)
+    int stem;                                 // producers build conv1's 7x7/2 im2col rows from the NCHW fp32 image
     int nprob, num_m_tiles, n_tiles_n, num_tiles;
     int KH, KW, Cin, cin_blocks, stride, pad, Cout, relu;
     const float *bias;
@@ -527,6 +528,51 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
         const int pt = threadIdx.x - 192;                  // 0..255
         Ring r(stages);
         int tb = 0;
+        if (P.stem) {
+            // conv1 (resnet.py:495, 7x7 stride 2 pad 3, 3 input channels) as a GEMM with K = 192 (147 used):
+            // A rows are gathered straight from the NCHW fp32 image (pr.offset), k = (kh*7 + kw)*3 + c
+            for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+                int pi, wb, hb, ib, nt;
+                decode_tile(P, tile, pi, wb, hb, ib, nt);
+                const Problem &pr = P.prob[pi];
+                const float *img = pr.offset;
+                for (int kb = 0; kb < 3; ++kb) {
+                    mbar_wait(&empty[r.stage], r.phase ^ 1);
+                    uint8_t *sa = smem + (size_t)r.stage * kStageBytes;
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int item = pt + it * 256, row = item >> 3, c16 = item & 7;
+                        const int iw = row & (pr.BW - 1), ih = (row >> pr.lbw) & (pr.BH - 1), ii = row >> (pr.lbw + pr.lbh);
+                        const int ow = wb * pr.BW + iw, oh = hb * pr.BH + ih, n = ib * pr.BI + ii;
+                        const bool ok = (ow < pr.Wo) && (oh < pr.Ho) && (n < pr.N);
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int k = kb * 64 + c16 * 8 + j;
+                            float x = 0.f;
+                            if (ok && k < 147) {
+                                const int tap = k / 3, c = k - tap * 3;
+                                const int kh = tap / 7, kw = tap - kh * 7;
+                                const int yy = oh * 2 - 3 + kh, xx = ow * 2 - 3 + kw;
+                                if (yy >= 0 && yy < pr.H && xx >= 0 && xx < pr.W)
+                                    x = __ldg(img + (((size_t)n * 3 + c) * pr.H + yy) * pr.W + xx);
+                            }
+                            v[j] = x;
+                        }
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int k2 = 0; k2 < 4; ++k2) {
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * k2], v[2 * k2 + 1]);
+                            pk[k2] = *reinterpret_cast<uint32_t *>(&b2);
+                        }
+                        *reinterpret_cast<uint4 *>(sa + (size_t)row * 128 + ((c16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(&full[r.stage]);
+                    r.next();
+                }
+            }
+        } else
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
             int pi, wb, hb, ib, nt;
             decode_tile(P, tile, pi, wb, hb, ib, nt);
@@ -665,7 +711,7 @@ int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st, int stag
         ORP_CUDA(cudaEventRecord(g_tc_ev[slot][0], st));
         double fl = 0;
         for (int i = 0; i < P.nprob; ++i)
-            fl += 2.0 * P.prob[i].N * P.prob[i].Ho * P.prob[i].Wo * (double)P.Cout * P.KH * P.KW * P.Cin;
+            fl += 2.0 * P.prob[i].N * P.prob[i].Ho * P.prob[i].Wo * (double)P.Cout * P.KH * P.KW * (P.stem ? 147 : P.Cin);
         g_tc_flops += fl;
         g_tc_trace[slot] = TcTrace{P.nprob, P.prob[0].N, P.prob[0].H, P.prob[0].W, P.Cin, P.Cout, P.KH, P.stride, DEFORM ? 1 : 0,
                                    BN, P.num_tiles, grid, fl};
@@ -702,10 +748,34 @@ extern "C" int orp_tc_timing_collect(float *total_ms, int *launches, double *flo
     return ORP_OK;
 }
 
+static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *w, int Cout, int Cout_padded, int KH,
+                            int KW, int Cin, int stride, int pad, const float *bias, int relu, int out_f32,
+                            int deform, int stem, void *stream);
+
 /* see include/orp_b200.h */
 extern "C" int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const void *w, int Cout, int Cout_padded, int KH,
                                int KW, int Cin, int stride, int pad, const float *bias, int relu, int out_f32,
                                int deform, void *stream)
+{
+    return conv2d_bf16_impl(nprob, probs, w, Cout, Cout_padded, KH, KW, Cin, stride, pad, bias, relu, out_f32, deform, 0, stream);
+}
+
+/* see include/orp_b200.h */
+extern "C" int orp_stem_conv_bf16(const float *img_nchw, int N, int H, int W, const void *w192, const float *bias, int relu,
+                                  void *out, void *stream)
+{
+    if (!img_nchw || !w192 || !out || N < 1) return fail(ORP_EINVAL, "stem_conv_bf16: bad arguments");
+    orp_tc_problem q;
+    memset(&q, 0, sizeof(q));
+    q.x = img_nchw;                       // never dereferenced as bf16: the producers read q.offset
+    q.offset = img_nchw;
+    q.N = N; q.H = H; q.W = W; q.out = out;
+    return conv2d_bf16_impl(1, &q, w192, 64, 64, 1, 1, 192, 1, 0, bias, relu, 0, 1, 1, stream);
+}
+
+static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *w, int Cout, int Cout_padded, int KH,
+                            int KW, int Cin, int stride, int pad, const float *bias, int relu, int out_f32,
+                            int deform, int stem, void *stream)
 {
     if (nprob < 1 || nprob > kMaxProb || !probs || !w) return fail(ORP_EINVAL, "conv2d_bf16: bad arguments");
     if (Cin % kBK) return fail(ORP_EINVAL, "conv2d_bf16: Cin must be a multiple of 64");
@@ -730,7 +800,7 @@ extern "C" int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const voi
     TcParams P;
     memset(&P, 0, sizeof(P));
     P.nprob = nprob; P.KH = KH; P.KW = KW; P.Cin = Cin; P.cin_blocks = Cin / kBK; P.stride = stride; P.pad = pad;
-    P.Cout = Cout; P.relu = relu; P.bias = bias;
+    P.Cout = Cout; P.relu = relu; P.bias = bias; P.stem = stem;
     P.n_tiles_n = Cout_padded / BN;
     int mt = 0;
     for (int i = 0; i < nprob; ++i) {
@@ -739,6 +809,7 @@ extern "C" int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const voi
         pr.N = q.N; pr.H = q.H; pr.W = q.W;
         pr.Ho = (q.H + 2 * pad - (KH - 1) - 1) / stride + 1;
         pr.Wo = (q.W + 2 * pad - (KW - 1) - 1) / stride + 1;
+        if (stem) { pr.Ho = (q.H + 6 - 7) / 2 + 1; pr.Wo = (q.W + 6 - 7) / 2 + 1; }
         if (pr.Ho <= 0 || pr.Wo <= 0 || !q.x || !q.out) return fail(ORP_EINVAL, "conv2d_bf16: bad problem");
         pr.BW = pow2_floor(pr.Wo < 128 ? pr.Wo : 128);
         if (stride * pr.BW > 256) pr.BW = 256 / stride;

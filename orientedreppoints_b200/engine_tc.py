@@ -38,19 +38,24 @@ class EngineTC:
     # ------------------------------------------------------------------ layers
     def prepare_input(self, img_nchw):
         img = img_nchw.to(self.device, torch.float32).contiguous()
-        n, c, h, w = img.shape
-        assert c == 3
-        ho, wo = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
-        cols = torch.empty((n, ho, wo, 192), dtype=torch.bfloat16, device=self.device)
-        _lib.check(self.lib.orp_stem_im2col_bf16(_lib.ptr(img), n, h, w, _lib.ptr(cols), _lib.current_stream_ptr()),
-                   "orp_stem_im2col_bf16")
-        return cols
+        assert img.shape[1] == 3
+        return img                                                   # the stem kernel reads the NCHW image directly
 
-    def stem(self, cols, L):
+    def stem(self, img, L, materialise=True):
         tc = self._stem_tc(L)
-        n, ho, wo, _ = cols.shape
+        n, _, h, w = img.shape
+        ho, wo = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
         y = torch.empty((n, ho, wo, 64), dtype=torch.bfloat16, device=self.device)
-        self._launch([cols], [y], tc, 64, 1, 1, 192, 1, 0, L.bias, True, False, False)
+        # default: im2col rows in HBM + plain GEMM (557 us per 4 tiles); the direct producer variant
+        # (orp_stem_conv_bf16, no HBM intermediate) is LSU-bound in its current scalar-gather form (1136 us)
+        if materialise:
+            cols = torch.empty((n, ho, wo, 192), dtype=torch.bfloat16, device=self.device)
+            _lib.check(self.lib.orp_stem_im2col_bf16(_lib.ptr(img), n, h, w, _lib.ptr(cols), _lib.current_stream_ptr()),
+                       "orp_stem_im2col_bf16")
+            self._launch([cols], [y], tc, 64, 1, 1, 192, 1, 0, L.bias, True, False, False)
+            return y
+        _lib.check(self.lib.orp_stem_conv_bf16(_lib.ptr(img), n, h, w, _lib.ptr(tc["w"]), _lib.ptr(L.bias), 1, _lib.ptr(y),
+                                               _lib.current_stream_ptr()), "orp_stem_conv_bf16")
         return y
 
     def _launch(self, xs, ys, tc, cout, kh, kw, cin, stride, pad, bias, relu, out_f32, deform, res=None, res32=None,

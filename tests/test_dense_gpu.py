@@ -197,3 +197,14 @@ def test_fused_postprocess_equals_torch_mirror_and_oracle(cuda, sd):
             rd, rl = tr.get_bboxes_single([c[0].permute(2, 0, 1) for c in cls], [r[0].permute(2, 0, 1).cpu() for r in ref],
                                           score_thr=thr, max_per_img=cap)
             assert torch.equal(labels[0, :counts[0]].cpu(), rl) and torch.equal(dets[0, :counts[0], -1].cpu(), rd[:, -1])
+
+
+def test_stem_conv_tc_direct_equals_materialised_im2col(cuda, sd):
+    from orientedreppoints_b200.detector import OrientedRepPointsDetector
+    det = OrientedRepPointsDetector(sd, 50, cuda, "bf16")
+    for (n, h, w) in ((2, 256, 320), (1, 250, 198)):
+        img = torch.randn(n, 3, h, w, generator=torch.Generator().manual_seed(h)).to(cuda)
+        a = det.eng.stem(img, det.stem, materialise=False)
+        b = det.eng.stem(img, det.stem, materialise=True)
+        assert a.shape == b.shape == (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 64)
+        assert torch.equal(a, b)

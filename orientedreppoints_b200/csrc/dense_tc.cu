@@ -529,36 +529,67 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
         Ring r(stages);
         int tb = 0;
         if (P.stem) {
-            // conv1 (resnet.py:495, 7x7 stride 2 pad 3, 3 input channels) as a GEMM with K = 192 (147 used):
-            // A rows are gathered straight from the NCHW fp32 image (pr.offset), k = (kh*7 + kw)*3 + c
+            // conv1 (resnet.py:495, 7x7 stride 2 pad 3, 3 input channels) as a GEMM with K = 192 (147 used),
+            // k = (kh*7 + kw)*3 + c.  Per tile the input patch ((2*BH+5) x (2*BW+5) pixels x 3 channels per image
+            // of the tile) is staged once in shared memory with coalesced loads of the NCHW fp32 image
+            // (pr.offset); the three 64-wide K blocks of A rows are then built from shared memory.
+            __shared__ float s_patch[5632];
+            __shared__ int s_koff[192];                                      // k -> offset inside the patch (-1: k >= 147)
+            {
+                const Problem &p0 = P.prob[0];
+                const int pw0 = 2 * p0.BW + 5, ph0 = 2 * p0.BH + 5;
+                if (pt < 192) {
+                    const int tap = pt / 3, c = pt - tap * 3, kh = tap / 7, kw = tap - kh * 7;
+                    s_koff[pt] = pt < 147 ? (c * ph0 + kh) * pw0 + kw : -1;
+                }
+            }
             for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
                 int pi, wb, hb, ib, nt;
                 decode_tile(P, tile, pi, wb, hb, ib, nt);
                 const Problem &pr = P.prob[pi];
                 const float *img = pr.offset;
+                const int pw = 2 * pr.BW + 5, ph = 2 * pr.BH + 5;            // patch extent per image
+                const int x0 = wb * pr.BW * 2 - 3, y0 = hb * pr.BH * 2 - 3;
+                const int per_img = 3 * ph * pw;
+                asm volatile("bar.sync 2, 256;" ::: "memory");               // previous tile's reads of the patch are done
+                {
+                    // one patch row (image, channel, y) per iteration: the row decode is warp-uniform, the loads of
+                    // different rows are independent (unrolled for memory-level parallelism) and coalesced along x
+                    const int nrows = pr.BI * 3 * ph;
+#pragma unroll 7
+                    for (int rowi = 0; rowi < nrows; ++rowi) {
+                        const int ii = rowi / (3 * ph), rem = rowi - ii * 3 * ph;
+                        const int c = rem / ph, py = rem - c * ph;
+                        const int n = ib * pr.BI + ii, yy = y0 + py;
+                        const bool rok = (n < pr.N) && (yy >= 0) && (yy < pr.H);
+                        const float *src = img + (((size_t)(rok ? n : 0) * 3 + c) * pr.H + (rok ? yy : 0)) * pr.W;
+                        for (int px = pt; px < pw; px += 256) {
+                            const int xx = x0 + px;
+                            s_patch[rowi * pw + px] = (rok && xx >= 0 && xx < pr.W) ? __ldg(src + xx) : 0.f;
+                        }
+                    }
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                int pbase[4];
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int row = (pt + it * 256) >> 3;
+                    const int iw = row & (pr.BW - 1), ih = (row >> pr.lbw) & (pr.BH - 1), ii = row >> (pr.lbw + pr.lbh);
+                    pbase[it] = ii * per_img + (ih * 2) * pw + iw * 2;
+                }
+                const int c16 = pt & 7;
                 for (int kb = 0; kb < 3; ++kb) {
                     mbar_wait(&empty[r.stage], r.phase ^ 1);
                     uint8_t *sa = smem + (size_t)r.stage * kStageBytes;
+                    const int4 o0 = *reinterpret_cast<const int4 *>(&s_koff[kb * 64 + c16 * 8]);
+                    const int4 o1 = *reinterpret_cast<const int4 *>(&s_koff[kb * 64 + c16 * 8 + 4]);
+                    const int off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
 #pragma unroll
                     for (int it = 0; it < 4; ++it) {
-                        const int item = pt + it * 256, row = item >> 3, c16 = item & 7;
-                        const int iw = row & (pr.BW - 1), ih = (row >> pr.lbw) & (pr.BH - 1), ii = row >> (pr.lbw + pr.lbh);
-                        const int ow = wb * pr.BW + iw, oh = hb * pr.BH + ih, n = ib * pr.BI + ii;
-                        const bool ok = (ow < pr.Wo) && (oh < pr.Ho) && (n < pr.N);
+                        const int row = (pt + it * 256) >> 3;
                         float v[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int k = kb * 64 + c16 * 8 + j;
-                            float x = 0.f;
-                            if (ok && k < 147) {
-                                const int tap = k / 3, c = k - tap * 3;
-                                const int kh = tap / 7, kw = tap - kh * 7;
-                                const int yy = oh * 2 - 3 + kh, xx = ow * 2 - 3 + kw;
-                                if (yy >= 0 && yy < pr.H && xx >= 0 && xx < pr.W)
-                                    x = __ldg(img + (((size_t)n * 3 + c) * pr.H + yy) * pr.W + xx);
-                            }
-                            v[j] = x;
-                        }
+                        for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? s_patch[pbase[it] + off[j]] : 0.f;
                         uint32_t pk[4];
 #pragma unroll
                         for (int k2 = 0; k2 < 4; ++k2) {

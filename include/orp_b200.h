@@ -261,6 +261,29 @@ int orp_gn_apply_bf16(const void *x, int N, int H, int W, int C, const double *s
                       const float *gamma, const float *beta, float eps, int relu, const void *up_src, void *y,
                       void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Swin-T backbone pieces (mmdet/models/backbones/swin_transformer.py); the Linear layers are
+ * orp_conv2d_bf16 1x1 convolutions (relu = 2 selects the exact GELU epilogue)
+ * ---------------------------------------------------------------------------------------- */
+
+/* nn.LayerNorm over the channel dimension of bf16 tokens [B,H,W,C]; the result is written into a grid
+ * [B,Hp,Wp,C] (Hp >= H, Wp >= W; rows/columns beyond H,W must be pre-zeroed by the caller) - the zero
+ * padding to multiples of the window size of SwinTransformerBlock.forward (:215-220). */
+int orp_layernorm_bf16(const void *x, int B, int H, int W, int C, const float *gamma, const float *beta, float eps,
+                       int Hp, int Wp, void *y, void *stream);
+/* (shifted) 7x7 window attention with relative position bias and the -100 region mask
+ * (WindowAttention.forward :122-154, BasicLayer mask :371-390): qkv bf16 [B,Hp,Wp,3C] (q|k|v, heads x 32),
+ * bias_table fp32 [169, heads]; out bf16 [B,H,W,C] at the original token positions (roll, window
+ * partition/reverse and the crop are index arithmetic). */
+int orp_window_attention_bf16(const void *qkv, int B, int H, int W, int Hp, int Wp, int C, int heads, int shift,
+                              const float *bias_table, float scale, void *out, void *stream);
+/* PatchEmbed.proj input rows (4x4 stride 4, :430-441): NCHW fp32 -> bf16 [B,ceil(H/4),ceil(W/4),64], k = c*16+kh*4+kw */
+int orp_patch_embed_rows_bf16(const float *img_nchw, int B, int H, int W, void *out, void *stream);
+/* PatchMerging gather (:288-293): [B,H,W,C] -> [B,ceil(H/2),ceil(W/2),4C] */
+int orp_patch_merge_gather_bf16(const void *x, int B, int H, int W, int C, void *y, void *stream);
+/* F.max_pool2d(x, 1, stride=2) (necks/fpn.py:163-165): [B,H,W,C] -> [B,ceil(H/2),ceil(W/2),C] */
+int orp_subsample2_bf16(const void *x, int B, int H, int W, int C, void *y, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -155,6 +155,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// epilogue activation: 0 none, 1 ReLU, 2 exact (erf) GELU as nn.GELU (swin_transformer.py:24-29)
+__device__ __forceinline__ float act_fn(float v, int act)
+{
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    return v;
+}
+
 struct Ring {
     int stage = 0;
     uint32_t phase = 0;
@@ -318,7 +326,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             if (P.bias) f += P.bias[c0 + j];
                             if (pr.res) f += __bfloat162float(pr.res[pix * P.Cout + c0 + j]);
                             if (rp) f += rp[j];
-                            if (P.relu) f = fmaxf(f, 0.f);
+                            f = act_fn(f, P.relu);
                             op[j] = f;
                         }
                     }
@@ -394,7 +402,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             }
                             if (P.relu) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                                for (int j = 0; j < 8; ++j) f[j] = act_fn(f[j], P.relu);
                             }
                             uint32_t pk[4];
 #pragma unroll
@@ -480,7 +488,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             }
                             if (P.relu) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                                for (int j = 0; j < 8; ++j) f[j] = act_fn(f[j], P.relu);
                             }
                             uint32_t pk[4];
 #pragma unroll
@@ -809,7 +817,8 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
                             int deform, int stem, void *stream)
 {
     if (nprob < 1 || nprob > kMaxProb || !probs || !w) return fail(ORP_EINVAL, "conv2d_bf16: bad arguments");
-    if (Cin % kBK) return fail(ORP_EINVAL, "conv2d_bf16: Cin must be a multiple of 64");
+    if (Cin % 8) return fail(ORP_EINVAL, "conv2d_bf16: Cin must be a multiple of 8 (16-byte channel rows)");
+    if (deform && !stem && (Cin % kBK)) return fail(ORP_EINVAL, "conv2d_bf16: deformable conv needs Cin % 64 == 0");
     if (Cout_padded % 32 || Cout_padded < Cout) return fail(ORP_EINVAL, "conv2d_bf16: padded Cout must be a multiple of 32");
     int rc = ensure_device();
     if (rc) return rc;
@@ -830,7 +839,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     }
     TcParams P;
     memset(&P, 0, sizeof(P));
-    P.nprob = nprob; P.KH = KH; P.KW = KW; P.Cin = Cin; P.cin_blocks = Cin / kBK; P.stride = stride; P.pad = pad;
+    P.nprob = nprob; P.KH = KH; P.KW = KW; P.Cin = Cin; P.cin_blocks = (Cin + kBK - 1) / kBK;   // a partial last block is zero-filled by TMA (A) and by the weight layout (B) P.stride = stride; P.pad = pad;
     P.Cout = Cout; P.relu = relu; P.bias = bias; P.stem = stem;
     P.n_tiles_n = Cout_padded / BN;
     int mt = 0;
@@ -866,7 +875,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
         }
     }
     {
-        const cuuint64_t K = (cuuint64_t)KH * KW * Cin;
+        const cuuint64_t K = (cuuint64_t)KH * KW * P.cin_blocks * kBK;   // per tap: cin_blocks x 64, zero padded
         cuuint64_t gdim[2] = {K, (cuuint64_t)Cout_padded};
         cuuint64_t gstr[1] = {K * 2};
         cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BN};

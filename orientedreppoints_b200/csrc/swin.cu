@@ -1,0 +1,267 @@
+// swin.cu - the non-GEMM pieces of the Swin-T backbone, NHWC bf16 tokens.
+//
+// Reference: mmdet/models/backbones/swin_transformer.py - PatchEmbed :430-446, SwinTransformerBlock :199-256
+// (norm1 -> zero pad to multiples of 7 -> cyclic shift -> 7x7 windows -> WindowAttention :122-154 -> reverse ->
+// crop -> residual; norm2 -> MLP), PatchMerging :272-299, BasicLayer mask :371-390.  All Linear layers run on the
+// tensor-core convolution kernel (dense_tc.cu) as 1x1 convolutions; here are LayerNorm (optionally scattering into
+// the zero-padded window grid), the window attention itself (shift, relative-position bias and the -100 region mask
+// are index arithmetic - no roll / partition / reverse copies), the 4x4 patch gather, the 2x2 merge gather and the
+// stride-2 subsample that max_pool2d(kernel 1, stride 2) is (necks/fpn.py:163-165).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace orp {
+namespace {
+
+// one warp per token; out may be a padded grid [B,Hp,Wp,C] (rows beyond H,W pre-zeroed by the caller)
+__global__ void __launch_bounds__(256)
+layernorm_bf16_kernel(const __nv_bfloat16 *__restrict__ x, int B, int H, int W, int C, const float *__restrict__ gamma,
+                      const float *__restrict__ beta, float eps, int Hp, int Wp, __nv_bfloat16 *__restrict__ y)
+{
+    const int lane = threadIdx.x & 31;
+    const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long ntok = (long long)B * H * W;
+    if (tok >= ntok) return;
+    const __nv_bfloat16 *px = x + tok * C;
+    float v[96];                                   // C <= 3072
+    const int per = (C + 31) / 32;
+    float s = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < per; ++i) {
+        const int c = lane + i * 32;
+        v[i] = c < C ? __bfloat162float(px[c]) : 0.f;
+        s += v[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < per; ++i) {
+        const int c = lane + i * 32;
+        const float d = c < C ? v[i] - mean : 0.f;
+        q += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)C + eps);
+    const int b = (int)(tok / ((long long)H * W)), hw = (int)(tok - (long long)b * H * W);
+    const int h = hw / W, w = hw - h * W;
+    __nv_bfloat16 *py = y + (((long long)b * Hp + h) * Wp + w) * C;
+#pragma unroll 4
+    for (int i = 0; i < per; ++i) {
+        const int c = lane + i * 32;
+        if (c < C) py[c] = __float2bfloat16_rn((v[i] - mean) * rstd * gamma[c] + beta[c]);
+    }
+}
+
+// qkv: [B,Hp,Wp,3C] (q | k | v, each heads x 32), out: [B,H,W,C] at the ORIGINAL (unshifted, uncropped-away) positions.
+// block = 64 threads = one (window, head); thread t < 49 owns query token t of the window.
+constexpr int kWin = 7, kTok = 49, kHd = 32;
+
+__global__ void __launch_bounds__(64)
+window_attention_kernel(const __nv_bfloat16 *__restrict__ qkv, int B, int H, int W, int Hp, int Wp, int C, int heads,
+                        int shift, const float *__restrict__ bias_table /* [169, heads] */, float scale,
+                        __nv_bfloat16 *__restrict__ out)
+{
+    __shared__ float sk[kTok][kHd + 1], sv[kTok][kHd + 1];
+    __shared__ int s_src[kTok], s_reg[kTok];
+    const int nww = Wp / kWin, nwh = Hp / kWin;
+    const int head = blockIdx.y;
+    const int wid = blockIdx.x % (nwh * nww), b = blockIdx.x / (nwh * nww);
+    const int wy = wid / nww, wx = wid - wy * nww;
+    const int t = threadIdx.x;
+    if (t < kTok) {
+        const int ty = t / kWin, tx = t - ty * kWin;
+        const int ys = wy * kWin + ty, xs = wx * kWin + tx;                 // coordinates in the shifted frame
+        int yo = ys + shift, xo = xs + shift;                                // roll(x, -shift): shifted[y] = x[(y + shift) % Hp]
+        if (yo >= Hp) yo -= Hp;
+        if (xo >= Wp) xo -= Wp;
+        s_src[t] = (b * Hp + yo) * Wp + xo;
+        // BasicLayer mask regions (:376-387): slices (0,-7), (-7,-3), (-3,None) of the shifted frame
+        const int hr = ys < Hp - kWin ? 0 : (ys < Hp - shift ? 1 : 2);
+        const int wr = xs < Wp - kWin ? 0 : (xs < Wp - shift ? 1 : 2);
+        s_reg[t] = shift > 0 ? hr * 3 + wr : 0;
+    }
+    __syncthreads();
+    for (int e = t; e < kTok * kHd; e += 64) {
+        const int j = e / kHd, d = e - j * kHd;
+        const __nv_bfloat16 *p = qkv + (long long)s_src[j] * (3 * C) + head * kHd + d;
+        sk[j][d] = __bfloat162float(p[C]);
+        sv[j][d] = __bfloat162float(p[2 * C]);
+    }
+    __syncthreads();
+    if (t >= kTok) return;
+    float q[kHd];
+    {
+        const __nv_bfloat16 *p = qkv + (long long)s_src[t] * (3 * C) + head * kHd;
+#pragma unroll
+        for (int d = 0; d < kHd; ++d) q[d] = __bfloat162float(p[d]) * scale;          // q = q * self.scale (:138)
+    }
+    const int ty = t / kWin, tx = t - ty * kWin;
+    float sc[kTok];
+    float mx = -3.0e38f;
+#pragma unroll 7
+    for (int j = 0; j < kTok; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < kHd; ++d) a = fmaf(q[d], sk[j][d], a);
+        const int jy = j / kWin, jx = j - jy * kWin;
+        a += bias_table[((ty - jy + kWin - 1) * (2 * kWin - 1) + (tx - jx + kWin - 1)) * heads + head];   // :107-118, :141-144
+        if (s_reg[t] != s_reg[j]) a += -100.0f;                                                            // :388-389
+        sc[j] = a;
+        mx = fmaxf(mx, a);
+    }
+    float den = 0.f;
+#pragma unroll 7
+    for (int j = 0; j < kTok; ++j) { sc[j] = expf(sc[j] - mx); den += sc[j]; }
+    const float inv = 1.0f / den;
+    float o[kHd];
+#pragma unroll
+    for (int d = 0; d < kHd; ++d) o[d] = 0.f;
+#pragma unroll 7
+    for (int j = 0; j < kTok; ++j) {
+        const float pj = sc[j] * inv;
+#pragma unroll
+        for (int d = 0; d < kHd; ++d) o[d] = fmaf(pj, sv[j][d], o[d]);
+    }
+    // window_reverse + roll(+shift) + crop: the token returns to its original position if that is inside H x W
+    const int src = s_src[t];
+    const int xo = src % Wp, yo = (src / Wp) % Hp;
+    if (yo < H && xo < W) {
+        __nv_bfloat16 *po = out + (((long long)b * H + yo) * W + xo) * C + head * kHd;
+#pragma unroll
+        for (int d = 0; d < kHd; d += 2) {
+            __nv_bfloat162 v2 = __floats2bfloat162_rn(o[d], o[d + 1]);
+            *reinterpret_cast<__nv_bfloat162 *>(po + d) = v2;
+        }
+    }
+}
+
+// PatchEmbed.proj input rows: NCHW fp32 image -> bf16 [B, ceil(H/4), ceil(W/4), 64], k = c*16 + kh*4 + kw (< 48), zero padded
+__global__ void __launch_bounds__(256)
+patch_embed_rows_kernel(const float *__restrict__ img, int B, int H, int W, int Ho, int Wo, __nv_bfloat16 *__restrict__ out)
+{
+    const long long total = (long long)B * Ho * Wo * 64;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i & 63);
+        const long long pix = i >> 6;
+        const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+        float v = 0.f;
+        if (k < 48) {
+            const int c = k >> 4, kh = (k >> 2) & 3, kw = k & 3;
+            const int y = oh * 4 + kh, x = ow * 4 + kw;
+            if (y < H && x < W) v = img[(((long long)b * 3 + c) * H + y) * W + x];      // F.pad with zeros (:432-436)
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// PatchMerging gather (:288-293): [B,H,W,C] -> [B,ceil(H/2),ceil(W/2),4C] = x(0::2,0::2) | x(1::2,0::2) | x(0::2,1::2) | x(1::2,1::2)
+__global__ void __launch_bounds__(256)
+patch_merge_gather_kernel(const __nv_bfloat16 *__restrict__ x, int B, int H, int W, int C, int Ho, int Wo,
+                          __nv_bfloat16 *__restrict__ y)
+{
+    const int c8 = C / 8;
+    const long long total = (long long)B * Ho * Wo * 4 * c8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % c8);
+        const int part = (int)((i / c8) & 3);
+        const long long pix = i / (4LL * c8);
+        const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+        const int yy = oh * 2 + (part & 1), xx = ow * 2 + (part >> 1);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (yy < H && xx < W) v = *reinterpret_cast<const uint4 *>(x + (((long long)b * H + yy) * W + xx) * C + cc * 8);
+        *reinterpret_cast<uint4 *>(y + pix * (4LL * C) + (long long)part * C + cc * 8) = v;
+    }
+}
+
+// max_pool2d(kernel_size=1, stride=2) == x[:, ::2, ::2, :]
+__global__ void __launch_bounds__(256)
+subsample2_kernel(const __nv_bfloat16 *__restrict__ x, int B, int H, int W, int C, int Ho, int Wo, __nv_bfloat16 *__restrict__ y)
+{
+    const int c8 = C / 8;
+    const long long total = (long long)B * Ho * Wo * c8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % c8);
+        const long long pix = i / c8;
+        const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+        reinterpret_cast<uint4 *>(y)[i] = *reinterpret_cast<const uint4 *>(x + (((long long)b * H + oh * 2) * W + ow * 2) * C + cc * 8);
+    }
+}
+
+int grid_for(long long items, int threads)
+{
+    long long g = (items + threads - 1) / threads;
+    const long long cap = 148 * 16;
+    return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace
+}  // namespace orp
+
+using namespace orp;
+
+extern "C" int orp_layernorm_bf16(const void *x, int B, int H, int W, int C, const float *gamma, const float *beta, float eps,
+                                  int Hp, int Wp, void *y, void *stream)
+{
+    if (!x || !y || !gamma || !beta || C < 1 || C > 3072 || Hp < H || Wp < W) return fail(ORP_EINVAL, "layernorm_bf16: bad arguments");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const long long ntok = (long long)B * H * W;
+    layernorm_bf16_kernel<<<(unsigned)((ntok + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16 *>(x), B, H, W, C, gamma, beta, eps, Hp, Wp, static_cast<__nv_bfloat16 *>(y));
+    ORP_LAUNCHED();
+    return ORP_OK;
+}
+
+extern "C" int orp_window_attention_bf16(const void *qkv, int B, int H, int W, int Hp, int Wp, int C, int heads, int shift,
+                                         const float *bias_table, float scale, void *out, void *stream)
+{
+    if (!qkv || !out || !bias_table || heads * kHd != C || Hp % kWin || Wp % kWin || shift < 0 || shift >= kWin)
+        return fail(ORP_EINVAL, "window_attention_bf16: needs 7x7 windows, head_dim 32, padded grid");
+    int rc = ensure_device();
+    if (rc) return rc;
+    dim3 grid(B * (Hp / kWin) * (Wp / kWin), heads);
+    window_attention_kernel<<<grid, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16 *>(qkv), B, H, W, Hp, Wp, C, heads, shift, bias_table, scale, static_cast<__nv_bfloat16 *>(out));
+    ORP_LAUNCHED();
+    return ORP_OK;
+}
+
+extern "C" int orp_patch_embed_rows_bf16(const float *img_nchw, int B, int H, int W, void *out, void *stream)
+{
+    if (!img_nchw || !out) return fail(ORP_EINVAL, "patch_embed_rows_bf16: bad arguments");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const int Ho = (H + 3) / 4, Wo = (W + 3) / 4;
+    patch_embed_rows_kernel<<<grid_for((long long)B * Ho * Wo * 64, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        img_nchw, B, H, W, Ho, Wo, static_cast<__nv_bfloat16 *>(out));
+    ORP_LAUNCHED();
+    return ORP_OK;
+}
+
+extern "C" int orp_patch_merge_gather_bf16(const void *x, int B, int H, int W, int C, void *y, void *stream)
+{
+    if (!x || !y || C % 8) return fail(ORP_EINVAL, "patch_merge_gather_bf16: bad arguments");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    patch_merge_gather_kernel<<<grid_for((long long)B * Ho * Wo * 4 * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16 *>(x), B, H, W, C, Ho, Wo, static_cast<__nv_bfloat16 *>(y));
+    ORP_LAUNCHED();
+    return ORP_OK;
+}
+
+extern "C" int orp_subsample2_bf16(const void *x, int B, int H, int W, int C, void *y, void *stream)
+{
+    if (!x || !y || C % 8) return fail(ORP_EINVAL, "subsample2_bf16: bad arguments");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    subsample2_kernel<<<grid_for((long long)B * Ho * Wo * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16 *>(x), B, H, W, C, Ho, Wo, static_cast<__nv_bfloat16 *>(y));
+    ORP_LAUNCHED();
+    return ORP_OK;
+}

@@ -139,6 +139,8 @@ class OrientedRepPointsDetector:
     # ------------------------------------------------------------------ weights
     def _load(self, sd):
         d = self.device
+        if self.depth == "swin_tiny":
+            return self._load_swin(sd)
 
         def folded(conv, bn, stride, pad, pad_cin_to=None):
             w, b = fold_bn(sd[conv + ".weight"].float(), sd[bn + ".weight"].float(), sd[bn + ".bias"].float(),
@@ -161,6 +163,10 @@ class OrientedRepPointsDetector:
                      Norm(sd, "neck.lateral_convs.%d.gn" % i, d)) for i in range(3)]
         self.fpn = [(ConvLayer(sd["neck.fpn_convs.%d.conv.weight" % i].float(), None, 2 if i >= 3 else 1, 1, d),
                      Norm(sd, "neck.fpn_convs.%d.gn" % i, d)) for i in range(5)]
+        self._load_head(sd)
+
+    def _load_head(self, sd):
+        d = self.device
         h = "bbox_head."
         self.cls_convs = [(ConvLayer(sd[h + "cls_convs.%d.conv.weight" % i].float(), None, 1, 1, d),
                            Norm(sd, h + "cls_convs.%d.gn" % i, d)) for i in range(3)]
@@ -174,9 +180,31 @@ class OrientedRepPointsDetector:
         self.ref_dcn = ConvLayer(sd[r + "pts_refine_conv.weight"].float(), None, 1, 1, d)
         self.ref_out = ConvLayer(sd[r + "pts_refine_out.weight"].float(), sd[r + "pts_refine_out.bias"].float(), 1, 0, d)
 
+    def _load_swin(self, sd):
+        """Swin-T + FPN(in [192,384,768], start_level 0, no extra convs: P6/P7 = stride-2 subsampling, fpn.py:163-165)"""
+        from .swin import SwinTiny
+        d = self.device
+        if self.eng.name != "bf16":
+            raise ValueError("the Swin-T backbone runs on the bf16 tensor-core engine")
+        self.swin = SwinTiny(sd, d, self.eng)
+        self.lat = [(ConvLayer(sd["neck.lateral_convs.%d.conv.weight" % i].float(), None, 1, 0, d),
+                     Norm(sd, "neck.lateral_convs.%d.gn" % i, d)) for i in range(3)]
+        self.fpn = [(ConvLayer(sd["neck.fpn_convs.%d.conv.weight" % i].float(), None, 1, 1, d),
+                     Norm(sd, "neck.fpn_convs.%d.gn" % i, d)) for i in range(3)]
+        self._load_head(sd)
+
     # ------------------------------------------------------------------ dense graph
     def extract_feat(self, img):
         e = self.eng
+        if self.depth == "swin_tiny":
+            c3, c4, c5 = self.swin.forward(img)
+            l2 = e.conv_gn(c5, *self.lat[2])
+            l1 = e.conv_gn(c4, *self.lat[1], up=l2)
+            l0 = e.conv_gn(c3, *self.lat[0], up=l1)
+            outs = [e.conv_gn(l0, *self.fpn[0]), e.conv_gn(l1, *self.fpn[1]), e.conv_gn(l2, *self.fpn[2])]
+            outs.append(self.swin.subsample2(outs[-1]))
+            outs.append(self.swin.subsample2(outs[-1]))
+            return outs
         x = e.prepare_input(img)
         x = e.maxpool(e.stem(x, self.stem))
         feats = []

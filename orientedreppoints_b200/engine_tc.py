@@ -19,11 +19,12 @@ class EngineTC:
     def _tc(self, L):
         if L.tc is None:
             w = L.w_raw                                              # [Cout, KH, KW, Cin] fp32 (unpadded Cin)
-            cout = w.shape[0]
+            cout, kh, kw, cin = w.shape
             cout_p = ((cout + 31) // 32) * 32
-            k = w.shape[1] * w.shape[2] * w.shape[3]
-            wp = torch.zeros((cout_p, k), dtype=torch.float32)
-            wp[:cout] = w.reshape(cout, k)
+            cin_p = ((cin + 63) // 64) * 64                          # per tap: whole 64-channel K blocks, zero padded
+            wp4 = torch.zeros((cout_p, kh, kw, cin_p), dtype=torch.float32)
+            wp4[:cout, :, :, :cin] = w
+            wp = wp4.reshape(cout_p, kh * kw * cin_p)
             L.tc = dict(w=wp.to(self.device, torch.bfloat16).contiguous(), cout_p=cout_p)
         return L.tc
 
@@ -74,6 +75,7 @@ class EngineTC:
         _lib.check(rc, "orp_conv2d_bf16")
 
     def conv_multi(self, xs, L, relu=False, residual=None, out_f32=False, residual_f32=None):
+        """relu: False/True, or 2 for the exact-GELU epilogue (Swin MLP)"""
         tc = self._tc(L)
         ys = []
         for x in xs:

@@ -148,7 +148,8 @@ gn_apply_bf16_kernel(const __nv_bfloat16 *__restrict__ x, int N, int H, int W, c
         if (up) {
             const int hw = (int)(pix % ((size_t)H * W));
             const int h = hw / W, w = hw - h * W;
-            const uint4 v = *reinterpret_cast<const uint4 *>(up + (((size_t)n * (H / 2) + h / 2) * (W / 2) + w / 2) * 256 + g * 8);
+            const int Hu = (H + 1) / 2, Wu = (W + 1) / 2;              // F.interpolate(size=prev_shape, mode='nearest'): src = floor(dst * in / out)
+            const uint4 v = *reinterpret_cast<const uint4 *>(up + (((size_t)n * Hu + (h * Hu) / H) * Wu + (w * Wu) / W) * 256 + g * 8);
             const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -220,7 +221,6 @@ extern "C" int orp_gn_apply_bf16(const void *x, int N, int H, int W, int C, cons
                                  void *stream)
 {
     if (!x || !y || !stats || !gamma || !beta || C != 256 || groups != 32) return fail(ORP_EINVAL, "gn_apply_bf16: needs C=256, 32 groups");
-    if (up_src && ((H & 1) || (W & 1))) return fail(ORP_EINVAL, "gn_apply_bf16: upsample-add needs even H, W");
     int rc = ensure_device();
     if (rc) return rc;
     const size_t total = (size_t)N * H * W * 32;

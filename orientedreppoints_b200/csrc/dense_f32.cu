@@ -232,7 +232,8 @@ gn_apply_f32_kernel(const float *__restrict__ x, int N, int H, int W, int C, con
         if (up) {
             const int hw = (int)(pix % ((size_t)H * W));
             const int h = hw / W, w = hw - h * W;
-            const float4 u = *reinterpret_cast<const float4 *>(up + (((size_t)n * (H / 2) + h / 2) * (W / 2) + w / 2) * C + c);
+            const int Hu = (H + 1) / 2, Wu = (W + 1) / 2;              // F.interpolate(size=prev_shape, mode='nearest'): src = floor(dst * in / out)
+            const float4 u = *reinterpret_cast<const float4 *>(up + (((size_t)n * Hu + (h * Hu) / H) * Wu + (w * Wu) / W) * C + c);
             o[0] += u.x; o[1] += u.y; o[2] += u.z; o[3] += u.w;
         }
         reinterpret_cast<float4 *>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
@@ -313,7 +314,6 @@ extern "C" int orp_gn_apply_f32(const float *x, int N, int H, int W, int C, cons
                                 void *stream)
 {
     if (!x || !y || !stats || !gamma || !beta || C % 4 || C % groups) return fail(ORP_EINVAL, "gn_apply_f32: bad arguments");
-    if (up_src && ((H & 1) || (W & 1))) return fail(ORP_EINVAL, "gn_apply_f32: upsample-add needs even H, W");
     int rc = ensure_device();
     if (rc) return rc;
     const size_t total4 = (size_t)N * H * W * C / 4;

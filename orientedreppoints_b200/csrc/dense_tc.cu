@@ -839,7 +839,9 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     }
     TcParams P;
     memset(&P, 0, sizeof(P));
-    P.nprob = nprob; P.KH = KH; P.KW = KW; P.Cin = Cin; P.cin_blocks = (Cin + kBK - 1) / kBK;   // a partial last block is zero-filled by TMA (A) and by the weight layout (B) P.stride = stride; P.pad = pad;
+    // a partial last channel block is zero-filled by TMA (A operand) and by the weight layout (B operand)
+    P.nprob = nprob; P.KH = KH; P.KW = KW; P.Cin = Cin; P.cin_blocks = (Cin + kBK - 1) / kBK;
+    P.stride = stride; P.pad = pad;
     P.Cout = Cout; P.relu = relu; P.bias = bias; P.stem = stem;
     P.n_tiles_n = Cout_padded / BN;
     int mt = 0;

@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--boxes", type=int, default=100000)
     ap.add_argument("--batch", type=int, default=None, help="tiles per step per GPU (r50_tile)")
     ap.add_argument("--precision", default=None, help="r50_tile arithmetic: bf16 | fp32")
+    ap.add_argument("--backbone", default=None, help="r50_tile workload backbone: r50 (default) | r101 | swin_tiny")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="r50_tile: eager launches instead of a CUDA graph")
     return ap.parse_args()

@@ -47,12 +47,41 @@ def conv_flops_per_tile(depth=50, size=1024):
     return fl
 
 
+def swin_flops_per_tile(size=1024):
+    """2*MACs of the Swin-T backbone (Linear layers + window attention on the 7-padded grids) + its FPN + the head."""
+    fl = 0.0
+    h = size // 4
+    fl += 2.0 * h * h * 96 * 48                                        # patch embed
+    for i, depth in enumerate((2, 2, 6, 2)):
+        c = 96 << i
+        hp = (h + 6) // 7 * 7
+        for _ in range(depth):
+            fl += 2.0 * hp * hp * 3 * c * c                            # qkv on the padded grid
+            fl += 2.0 * hp * hp * 49 * c * 2                           # QK^T and PV
+            fl += 2.0 * h * h * c * c                                  # proj
+            fl += 2.0 * h * h * 8 * c * c                              # MLP
+        if i < 3:
+            fl += 2.0 * (h // 2) * (h // 2) * 4 * c * 2 * c            # patch merging reduction
+            h //= 2
+    lv = [size // 8, size // 16, size // 32, size // 64, size // 128]
+    for hw, cin in zip(lv[:3], (192, 384, 768)):
+        fl += 2.0 * hw * hw * 256 * cin + 2.0 * hw * hw * 256 * 256 * 9
+    loc = sum(v * v for v in lv)
+    fl += loc * 2.0 * (6 * 256 * 256 * 9 + 256 * 256 * 9 + 256 * 18 + 2 * 256 * 256 * 9 + 256 * 15 + 256 * 18)
+    return fl
+
+
 def run(args, rank, world, local, benchmod):
     dev = torch.device("cuda", local)
-    batch = args.batch or 4
+    batch = args.batch or 8
     precision = args.precision or "bf16"
-    depth = 50
-    sd = random_state_dict(depth, seed=0, reference_init=True)
+    backbone = getattr(args, "backbone", None) or "r50"
+    if backbone == "swin_tiny":
+        from .swin import random_swin_state_dict
+        depth, sd = "swin_tiny", random_swin_state_dict(0)
+    else:
+        depth = int(backbone[1:])
+        sd = random_state_dict(depth, seed=0, reference_init=True)
     det = OrientedRepPointsDetector(sd, depth, dev, precision, test_cfg=dict(score_thr=0.0))
     g = torch.Generator().manual_seed(1000 + rank)
     img_host = torch.randn(batch, 3, 1024, 1024, generator=g).pin_memory()
@@ -132,13 +161,14 @@ def run(args, rank, world, local, benchmod):
     d2h = sum(int(a.nbytes) for per_img in out for a in per_img)
 
     pk = benchmod.peaks()
-    fl_tile = conv_flops_per_tile(depth)
+    fl_tile = swin_flops_per_tile() if depth == "swin_tiny" else conv_flops_per_tile(depth)
     line = {
         "metric": "1024x1024 tiles/sec", "value": world * batch / (ms_step * 1e-3), "unit": "tiles/s", "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": precision, "data": "synthetic",
-        "config": {"workload": "R-%d FPN OrientedRepPoints, %d synthetic 1024x1024 tile(s) per GPU per step, random-init "
-                               "weights, score_thr=0 (80160 NMS candidates per tile), rnms iou 0.4, max_per_img 2000" % (depth, batch),
+        "config": {"workload": "%s FPN OrientedRepPoints, %d synthetic 1024x1024 tile(s) per GPU per step, random-init "
+                               "weights, score_thr=0 (80160 NMS candidates per tile), rnms iou 0.4, max_per_img 2000"
+                               % ("Swin-T" if depth == "swin_tiny" else "R-%d" % depth, batch),
                    "tiles_per_gpu_per_step": batch, "detections_per_tile": ndet[:4],
                    "l2": "512 MiB flush write between timed steps", "gflop_per_tile": fl_tile / 1e9,
                    "cuda_graph": "dense graph (backbone+FPN+head) replayed as one CUDA graph" if use_graph else "eager launches",

@@ -208,3 +208,21 @@ def test_stem_conv_tc_direct_equals_materialised_im2col(cuda, sd):
         b = det.eng.stem(img, det.stem, materialise=True)
         assert a.shape == b.shape == (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 64)
         assert torch.equal(a, b)
+
+
+def test_r101_graph_bf16_vs_f32_engine(cuda):
+    """BASELINE.json configs[3] backbone: same code path with STAGE_BLOCKS[101] = (3, 4, 23, 3)"""
+    from orientedreppoints_b200.detector import OrientedRepPointsDetector
+    from orientedreppoints_b200.weights import random_state_dict
+    sd101 = random_state_dict(101, seed=3, reference_init=False)
+    assert "backbone.layer3.22.conv3.weight" in sd101
+    d32 = OrientedRepPointsDetector(sd101, 101, cuda, "fp32")
+    d16 = OrientedRepPointsDetector(sd101, 101, cuda, "bf16")
+    img = torch.randn(1, 3, 192, 256, generator=torch.Generator().manual_seed(1)).to(cuda)
+    o32, f32 = d32.forward_dense(img)
+    o16, f16 = d16.forward_dense(img)
+    for lvl in range(5):
+        assert _rel(f16[lvl].float(), f32[lvl]) < 0.08, lvl
+        for k in range(3):
+            a, b = o16[lvl][k], o32[lvl][k]
+            assert float((a - b).abs().max()) < 0.1 * max(1.0, float(b.abs().max())), (lvl, k)

@@ -234,3 +234,13 @@ def test_result_merge_gpu_vs_restated_reference(cuda, po, tmp_path):
     assert rm.py_cpu_nms_poly(np.zeros((0, 9)), 0.1) == []
     d = po.gen_rotated_boxes(500, seed=3)
     assert rm.py_cpu_nms_poly(d.astype(np.float64), 0.3) == [int(i) for i in po.nms_poly_f64(d, 0.3)]
+
+
+def test_box_iou_rotated_vs_compiled_reference(cuda, golden):
+    """golden minted from the reference's box_iou_rotated_cpu.cpp (tests/golden/gen_golden_box_iou_rotated.py)"""
+    from orientedreppoints_b200.ops import box_iou_rotated
+    g = golden("box_iou_rotated.npz")
+    out = box_iou_rotated(_t(g["b1"], cuda), _t(g["b2"], cuda)).cpu().numpy()
+    assert out.shape == g["iou"].shape and out.dtype == np.float32
+    assert np.abs(out - g["iou"]).max() < 1e-4            # north_star tolerance; both are fp32 centre-shifted evaluations
+    assert (g["iou"] > 0.05).sum() > 100

@@ -22,28 +22,47 @@ __device__ __forceinline__ float2 unpack2(uint32_t u)
 // img: NCHW fp32 [N,3,H,W] (the layout the reference feeds its backbone) -> bf16 [N,Ho,Wo,192]
 // with k = (kh*7 + kw)*3 + c for k < 147 and zeros above: conv1 (resnet.py:495) becomes a 1x1
 // convolution over 192 channels on the tensor cores.
+// One block = 64 consecutive output pixels of one output row: the 7 x 133 x 3 input patch is staged in shared
+// memory with coalesced loads, then every thread emits whole 16-byte chunks (8 k-values) - consecutive threads
+// write consecutive chunks of the same 384-byte row, so both sides of the kernel move full cache lines.
+constexpr int kStemPix = 64;
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const float *__restrict__ img, int N, int H, int W, int Ho, int Wo, __nv_bfloat16 *__restrict__ out)
 {
-    const size_t total = (size_t)N * Ho * Wo * 24;   // 24 chunks of 8 k-values
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int ck = (int)(i % 24);
-        const size_t pix = i / 24;
-        const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho), n = (int)(pix / ((size_t)Wo * Ho));
+    constexpr int PW = 2 * kStemPix + 5;                 // 133 input columns
+    __shared__ float s_p[3 * 7 * PW];
+    __shared__ __align__(16) int s_koff[192];
+    const int t = threadIdx.x;
+    const int wblocks = (Wo + kStemPix - 1) / kStemPix;
+    const int wb = blockIdx.x % wblocks;
+    const int oh = (blockIdx.x / wblocks) % Ho, n = blockIdx.x / (wblocks * Ho);
+    const int ow0 = wb * kStemPix, x0 = ow0 * 2 - 3, y0 = oh * 2 - 3;
+    if (t < 192) {
+        const int tap = t / 3, c = t - tap * 3, kh = tap / 7, kw = tap - kh * 7;
+        s_koff[t] = t < 147 ? (c * 7 + kh) * PW + kw : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < 21; ++r) {                        // (channel, patch row): warp-uniform decode, coalesced along x
+        const int c = r / 7, py = r - c * 7, yy = y0 + py;
+        const bool rok = yy >= 0 && yy < H;
+        const float *src = img + (((size_t)n * 3 + c) * H + (rok ? yy : 0)) * W;
+        if (t < PW) {
+            const int xx = x0 + t;
+            s_p[r * PW + t] = (rok && xx >= 0 && xx < W) ? __ldg(src + xx) : 0.f;
+        }
+    }
+    __syncthreads();
+    const int npix = min(kStemPix, Wo - ow0);
+    __nv_bfloat16 *orow = out + (((size_t)n * Ho + oh) * Wo + ow0) * 192;
+    for (int item = t; item < npix * 24; item += 256) {
+        const int px = item / 24, ck = item - px * 24;
+        const int4 o0 = *reinterpret_cast<const int4 *>(&s_koff[ck * 8]), o1 = *reinterpret_cast<const int4 *>(&s_koff[ck * 8 + 4]);
+        const int off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+        const float *pb = s_p + px * 2;
         float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = ck * 8 + j;
-            float x = 0.f;
-            if (k < 147) {
-                const int tap = k / 3, c = k - tap * 3;
-                const int kh = tap / 7, kw = tap - kh * 7;
-                const int ih = oh * 2 - 3 + kh, iw = ow * 2 - 3 + kw;
-                if (ih >= 0 && ih < H && iw >= 0 && iw < W) x = img[(((size_t)n * 3 + c) * H + ih) * W + iw];
-            }
-            v[j] = x;
-        }
-        reinterpret_cast<uint4 *>(out)[i] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+        for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? pb[off[j]] : 0.f;
+        *reinterpret_cast<uint4 *>(orow + (size_t)item * 8) = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
     }
 }
 
@@ -180,8 +199,8 @@ extern "C" int orp_stem_im2col_bf16(const float *img_nchw, int N, int H, int W, 
     int rc = ensure_device();
     if (rc) return rc;
     const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
-    const size_t total = (size_t)N * Ho * Wo * 24;
-    stem_im2col_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    const int wblocks = (Wo + kStemPix - 1) / kStemPix;
+    stem_im2col_kernel<<<(unsigned)((size_t)N * Ho * wblocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         img_nchw, N, H, W, Ho, Wo, static_cast<__nv_bfloat16 *>(out));
     ORP_LAUNCHED();
     return ORP_OK;

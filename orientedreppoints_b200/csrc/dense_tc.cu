@@ -542,7 +542,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
             // of the tile) is staged once in shared memory with coalesced loads of the NCHW fp32 image
             // (pr.offset); the three 64-wide K blocks of A rows are then built from shared memory.
             __shared__ float s_patch[5632];
-            __shared__ int s_koff[192];                                      // k -> offset inside the patch (-1: k >= 147)
+            __shared__ __align__(16) int s_koff[192];                                      // k -> offset inside the patch (-1: k >= 147)
             {
                 const Problem &p0 = P.prob[0];
                 const int pw0 = 2 * p0.BW + 5, ph0 = 2 * p0.BH + 5;

@@ -236,6 +236,9 @@ typedef struct {
     const void *residual_bf16;  /* optional bf16 NHWC [N,Ho,Wo,Cout], added before ReLU               */
     const float *residual_f32;  /* optional fp32 NHWC [N,Ho,Wo,Cout] (head: refine += init, :168)     */
     const float *offset;        /* deformable only: fp32 [N,Ho,Wo,2*KH*KW], (dy,dx) per tap           */
+    double *gn_stats;           /* optional: double [N,32,2] (sum, sum of squares) of the bf16 output,
+                                   zeroed by the caller - the GroupNorm(32) statistics of the layer,
+                                   accumulated in the convolution's epilogue when the shape allows    */
 } orp_tc_problem;
 
 /* y = relu?(conv(x, w) + bias + residual) for up to 5 problems sharing the weights.  deform != 0:

@@ -30,7 +30,7 @@ class NmsStats(ctypes.Structure):
 
 class TcProblem(ctypes.Structure):
     _fields_ = [("x", _vp), ("N", _i), ("H", _i), ("W", _i), ("out", _vp), ("residual_bf16", _vp),
-                ("residual_f32", _vp), ("offset", _vp)]
+                ("residual_f32", _vp), ("offset", _vp), ("gn_stats", _vp)]
 
 
 # name -> (restype, argtypes); every symbol include/orp_b200.h declares

@@ -50,6 +50,7 @@ struct Problem {
     const float *res32;                       // optional fp32 residual (head: refine += init)
     const __nv_bfloat16 *x;                   // activation base (deformable variant)
     const float *offset;                      // deformable: [N,Ho,Wo,2*taps] fp32
+    double *gn_stats;                         // optional [N, 32, 2] (sum, sum of squares) of the output, GroupNorm(32)
 };
 
 struct alignas(64) TcParams {
@@ -59,6 +60,7 @@ struct alignas(64) TcParams {
     CUtensorMap tmRes[kMaxProb];              // bf16 residual tensors, same boxes
     Problem prob[kMaxProb];
     int tma_epi, epi_bufs;                    // TMA epilogue on/off; output staging buffers (1 or 2)
+    int gn_fused;                             // GroupNorm statistics accumulated in the TMA epilogue (Cout == 256)
     int stem;                                 // producers build conv1's 7x7/2 im2col rows from the NCHW fp32 image
     int nprob, num_m_tiles, n_tiles_n, num_tiles;
     int KH, KW, Cin, cin_blocks, stride, pad, Cout, relu;
@@ -373,6 +375,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                         tcgen05_fence_after();
                     }
                     if (pr.res) mbar_wait(&res_bar[rb], (uint32_t)((tma_g >> 1) & 1));
+                    float gn_s = 0.f, gn_q = 0.f;
                     uint8_t *orow = Obuf + (size_t)ob * 16384 + (size_t)rrow * 128;
                     const uint8_t *rrow_p = Rbuf + (size_t)rb * 16384 + (size_t)rrow * 128;
 #pragma unroll
@@ -411,6 +414,29 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                                 pk[k] = *reinterpret_cast<uint32_t *>(&b2);
                             }
                             *reinterpret_cast<uint4 *>(orow + sw) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            if (P.gn_fused) {
+                                // one 16-byte chunk = 8 channels = one GroupNorm group (Cout 256 / 32 groups)
+                                float gs = 0.f, gq = 0.f;
+                                if (valid) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) { gs += f[j]; gq = fmaf(f[j], f[j], gq); }
+                                }
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) {
+                                    gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                                    gq += __shfl_xor_sync(0xffffffffu, gq, o);
+                                }
+                                if (lane == c16) { gn_s = gs; gn_q = gq; }      // lane g keeps group g of this pass
+                            }
+                        }
+                    }
+                    if (P.gn_fused && lane < 8) {
+                        // the 32 rows of a warp belong to one image (host guarantees BW*BH >= 32)
+                        const int n_img = ib * pr.BI + ((q * 32) >> (pr.lbw + pr.lbh));
+                        if (n_img < pr.N) {
+                            double *st = pr.gn_stats + ((size_t)n_img * 32 + (size_t)(nt * BN + half * 64) / 8 + lane) * 2;
+                            atomicAdd(st, (double)gn_s);
+                            atomicAdd(st + 1, (double)gn_q);
                         }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -863,7 +889,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
         pr.tile_start = mt;
         mt += pr.tiles_w * pr.tiles_h * pr.tiles_i;
         pr.out = q.out; pr.res = static_cast<const __nv_bfloat16 *>(q.residual_bf16); pr.res32 = q.residual_f32;
-        pr.x = static_cast<const __nv_bfloat16 *>(q.x); pr.offset = q.offset;
+        pr.x = static_cast<const __nv_bfloat16 *>(q.x); pr.offset = q.offset; pr.gn_stats = q.gn_stats;
         if (deform && !q.offset) return fail(ORP_EINVAL, "conv2d_bf16: deformable conv needs offsets");
         if (!deform) {
             cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.N};
@@ -894,6 +920,13 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     for (int i = 0; i < nprob; ++i) any_res = any_res || (probs[i].residual_bf16 != nullptr);
     P.tma_epi = (!out_f32 && (Cout % 64 == 0) && BN >= 64) ? 1 : 0;
     if (getenv("ORP_TC_NO_TMA_EPI")) P.tma_epi = 0;
+    // GroupNorm statistics: fused into the TMA epilogue when every warp's 32 rows lie in one image
+    bool want_gn = false, gn_ok = (P.tma_epi != 0) && Cout == 256 && !bias && !relu;
+    for (int i = 0; i < nprob; ++i) {
+        want_gn = want_gn || (probs[i].gn_stats != nullptr);
+        if (P.prob[i].BW * P.prob[i].BH < 32) gn_ok = false;
+    }
+    P.gn_fused = (want_gn && gn_ok) ? 1 : 0;
     const bool mem_bound = any_res || (KH * KW * (Cin / kBK) <= 8);
     P.epi_bufs = mem_bound ? 2 : 1;
     if (P.tma_epi) {
@@ -929,15 +962,29 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     int stages = (int)((227 * 1024 - 4096 - 1024 - staging) / stage_bytes);
     if (stages > kStagesMax) stages = kStagesMax;
     if (deform && stages > 3) stages = 3;     // leave L1 capacity for the bilinear gather (corner reuse between neighbouring pixels)
+    int lrc = ORP_EINVAL;
+    bool launched = false;
 #define ORP_TC_DISPATCH(BNV)                                                                     \
-    if (BN == BNV) {                                                                             \
-        if (deform) return out_f32 ? launch_tc<BNV, true, true>(P, stages, grid, st, staging) : launch_tc<BNV, false, true>(P, stages, grid, st, staging); \
-        return out_f32 ? launch_tc<BNV, true, false>(P, stages, grid, st, staging) : launch_tc<BNV, false, false>(P, stages, grid, st, staging);          \
+    if (!launched && BN == BNV) {                                                                \
+        launched = true;                                                                         \
+        if (deform) lrc = out_f32 ? launch_tc<BNV, true, true>(P, stages, grid, st, staging) : launch_tc<BNV, false, true>(P, stages, grid, st, staging); \
+        else lrc = out_f32 ? launch_tc<BNV, true, false>(P, stages, grid, st, staging) : launch_tc<BNV, false, false>(P, stages, grid, st, staging);       \
     }
     ORP_TC_DISPATCH(256)
     ORP_TC_DISPATCH(128)
     ORP_TC_DISPATCH(64)
     ORP_TC_DISPATCH(32)
 #undef ORP_TC_DISPATCH
-    return fail(ORP_EINVAL, "conv2d_bf16: unsupported tile width");
+    if (!launched) return fail(ORP_EINVAL, "conv2d_bf16: unsupported tile width");
+    if (lrc) return lrc;
+    if (want_gn && !P.gn_fused) {
+        // statistics requested but not fusable for this shape: separate pass over the bf16 output
+        if (out_f32 || Cout != 256) return fail(ORP_EINVAL, "conv2d_bf16: gn_stats needs a bf16 output with 256 channels");
+        for (int i = 0; i < nprob; ++i)
+            if (probs[i].gn_stats) {
+                int r2 = orp_gn_stats_bf16(P.prob[i].out, P.prob[i].N, P.prob[i].Ho * P.prob[i].Wo, 256, 32, probs[i].gn_stats, stream);
+                if (r2) return r2;
+            }
+    }
+    return ORP_OK;
 }

@@ -60,7 +60,7 @@ class EngineTC:
         return y
 
     def _launch(self, xs, ys, tc, cout, kh, kw, cin, stride, pad, bias, relu, out_f32, deform, res=None, res32=None,
-                offsets=None):
+                offsets=None, stats=None):
         n = len(xs)
         arr = (_lib.TcProblem * n)()
         for i in range(n):
@@ -70,12 +70,14 @@ class EngineTC:
             arr[i].residual_bf16 = res[i].data_ptr() if res is not None else None
             arr[i].residual_f32 = res32[i].data_ptr() if res32 is not None else None
             arr[i].offset = offsets[i].data_ptr() if offsets is not None else None
+            arr[i].gn_stats = stats[i].data_ptr() if stats is not None else None
         rc = self.lib.orp_conv2d_bf16(n, arr, _lib.ptr(tc["w"]), cout, tc["cout_p"], kh, kw, cin, stride, pad,
                                       _lib.ptr(bias), int(relu), int(out_f32), int(deform), _lib.current_stream_ptr())
         _lib.check(rc, "orp_conv2d_bf16")
 
-    def conv_multi(self, xs, L, relu=False, residual=None, out_f32=False, residual_f32=None):
-        """relu: False/True, or 2 for the exact-GELU epilogue (Swin MLP)"""
+    def conv_multi(self, xs, L, relu=False, residual=None, out_f32=False, residual_f32=None, stats=None):
+        """relu: False/True, or 2 for the exact-GELU epilogue (Swin MLP); stats: per-problem double [N,32,2] tensors
+        (zeroed) that receive the GroupNorm statistics of the outputs"""
         tc = self._tc(L)
         ys = []
         for x in xs:
@@ -86,17 +88,18 @@ class EngineTC:
             ys.append(torch.empty((n, ho, wo, L.cout), dtype=torch.float32 if out_f32 else torch.bfloat16,
                                   device=self.device))
         self._launch(xs, ys, tc, L.cout, L.kh, L.kw, L.w_raw.shape[3], L.stride, L.pad, L.bias, relu, out_f32, False,
-                     res=residual, res32=residual_f32)
+                     res=residual, res32=residual_f32, stats=stats)
         return ys
 
     def conv(self, x, L, relu=False, residual=None, out_f32=False):
         return self.conv_multi([x], L, relu, None if residual is None else [residual], out_f32)[0]
 
-    def gn(self, x, norm, relu=False, up=None):
+    def gn(self, x, norm, relu=False, up=None, stats=None):
         n, h, w, c = x.shape
-        stats = torch.zeros((n, 32, 2), dtype=torch.float64, device=self.device)
         st = _lib.current_stream_ptr()
-        _lib.check(self.lib.orp_gn_stats_bf16(_lib.ptr(x), n, h * w, c, 32, _lib.ptr(stats), st), "orp_gn_stats_bf16")
+        if stats is None:
+            stats = torch.zeros((n, 32, 2), dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.orp_gn_stats_bf16(_lib.ptr(x), n, h * w, c, 32, _lib.ptr(stats), st), "orp_gn_stats_bf16")
         y = torch.empty_like(x)
         _lib.check(self.lib.orp_gn_apply_bf16(_lib.ptr(x), n, h, w, c, _lib.ptr(stats), 32, _lib.ptr(norm.gamma),
                                               _lib.ptr(norm.beta), 1e-5, int(relu), _lib.ptr(up), _lib.ptr(y), st),
@@ -104,10 +107,14 @@ class EngineTC:
         return y
 
     def conv_gn(self, x, L, norm, relu=False, up=None):
-        return self.gn(self.conv(x, L), norm, relu=relu, up=up)
+        st = torch.zeros((x.shape[0], 32, 2), dtype=torch.float64, device=self.device)
+        y = self.conv_multi([x], L, stats=[st])[0]                     # statistics come out of the conv epilogue
+        return self.gn(y, norm, relu=relu, up=up, stats=st)
 
     def conv_gn_multi(self, xs, L, norm, relu=False):
-        return [self.gn(y, norm, relu=relu) for y in self.conv_multi(xs, L)]
+        sts = torch.zeros((len(xs), xs[0].shape[0], 32, 2), dtype=torch.float64, device=self.device)
+        ys = self.conv_multi(xs, L, stats=[sts[i] for i in range(len(xs))])
+        return [self.gn(y, norm, relu=relu, stats=sts[i]) for i, y in enumerate(ys)]
 
     def maxpool(self, x):
         n, h, w, c = x.shape

@@ -204,7 +204,8 @@ struct FastRes {
 };
 
 // a[8], b[8]: quads already translated to a pair-local origin.  FMAs allowed here.
-__device__ __forceinline__ FastRes fast_quad_pair(const float *a, const float *b)
+template <int S>
+__device__ __forceinline__ FastRes fast_quad_pair_s(const float *a, const float *b, float *w)
 {
     float ax[4], ay[4], bx[4], by[4];
     float L = 0.f;
@@ -227,38 +228,50 @@ __device__ __forceinline__ FastRes fast_quad_pair(const float *a, const float *b
         t = bx[0]; bx[0] = bx[3]; bx[3] = t; t = by[0]; by[0] = by[3]; by[3] = t;
         t = bx[1]; bx[1] = bx[2]; bx[2] = t; t = by[1]; by[1] = by[2]; by[2] = t;
     }
-    float px[10], py[10], qx[10], qy[10];
-    int n = 4;
+    // two ping-pong vertex rings of <= 9 points in the caller's scratch (element k of array j at w[(j*10 + k) * S]):
+    // shared memory with S = blockDim for the NMS sweep (no local-memory traffic), a local array with S = 1 elsewhere
+    int n = 4, src = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { px[i] = ax[i]; py[i] = ay[i]; }
+    for (int i = 0; i < 4; ++i) { w[(0 * 10 + i) * S] = ax[i]; w[(1 * 10 + i) * S] = ay[i]; }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+        if (n == 0) break;
         const float ex = bx[(k + 1) & 3] - bx[k], ey = by[(k + 1) & 3] - by[k];
         const float ox = bx[k], oy = by[k];
+        float *sx = w + (src * 20) * S, *sy = w + (src * 20 + 10) * S;
+        float *dx = w + ((src ^ 1) * 20) * S, *dy = w + ((src ^ 1) * 20 + 10) * S;
         int m = 0;
-        if (n > 0) {
-            float dc = ex * (py[0] - oy) - ey * (px[0] - ox);
-            for (int i = 0; i < n; ++i) {
-                const int j = (i + 1 == n) ? 0 : i + 1;
-                const float dn = ex * (py[j] - oy) - ey * (px[j] - ox);
-                const bool inc = dc >= 0.f, inn = dn >= 0.f;
-                if (inc) { qx[m] = px[i]; qy[m] = py[i]; ++m; }
-                if (inc != inn) {
-                    const float t = dc / (dc - dn);
-                    qx[m] = fmaf(t, px[j] - px[i], px[i]);
-                    qy[m] = fmaf(t, py[j] - py[i], py[i]);
-                    ++m;
-                }
-                dc = dn;
+        const float fx = sx[0], fy = sy[0];
+        float cx = fx, cy = fy;
+        float dc = ex * (cy - oy) - ey * (cx - ox);
+        for (int i = 0; i < n; ++i) {
+            const bool last = (i + 1 == n);
+            const float nx = last ? fx : sx[(i + 1) * S], ny = last ? fy : sy[(i + 1) * S];
+            const float dn = ex * (ny - oy) - ey * (nx - ox);
+            const bool inc = dc >= 0.f, inn = dn >= 0.f;
+            if (inc) { dx[m * S] = cx; dy[m * S] = cy; ++m; }
+            if (inc != inn) {
+                const float t = dc / (dc - dn);
+                dx[m * S] = fmaf(t, nx - cx, cx);
+                dy[m * S] = fmaf(t, ny - cy, cy);
+                ++m;
             }
+            cx = nx; cy = ny; dc = dn;
         }
         n = m < 9 ? m : 9;
-        for (int i = 0; i < n; ++i) { px[i] = qx[i]; py[i] = qy[i]; }
+        src ^= 1;
     }
     float si = 0.f;
-    for (int i = 0; i < n; ++i) {
-        const int j = (i + 1 == n) ? 0 : i + 1;
-        si += px[i] * py[j] - py[i] * px[j];
+    if (n > 0) {
+        const float *sx = w + (src * 20) * S, *sy = w + (src * 20 + 10) * S;
+        const float fx = sx[0], fy = sy[0];
+        float cx = fx, cy = fy;
+        for (int i = 0; i < n; ++i) {
+            const bool last = (i + 1 == n);
+            const float nx = last ? fx : sx[(i + 1) * S], ny = last ? fy : sy[(i + 1) * S];
+            si += cx * ny - cy * nx;
+            cx = nx; cy = ny;
+        }
     }
     FastRes r;
     r.inter = 0.5f * fabsf(si);
@@ -269,6 +282,13 @@ __device__ __forceinline__ FastRes fast_quad_pair(const float *a, const float *b
     // in tests/test_nms_gpu.py::test_fast_clip_error_envelope).
     r.err = 64.f * 5.9604645e-08f * L * L;
     return r;
+}
+
+// convenience form with thread-local scratch
+__device__ __forceinline__ FastRes fast_quad_pair(const float *a, const float *b)
+{
+    float w[40];
+    return fast_quad_pair_s<1>(a, b, w);
 }
 
 }  // namespace orp

@@ -134,9 +134,10 @@ __device__ __noinline__ bool decide_fp64(const Quad &A, const Quad &B, double th
 }
 
 // returns true iff the reference's fp64 IoU of (A,B) suppresses at thr
+template <int S>
 __device__ __forceinline__ bool decide_exact(const Quad &A, const Quad &B, const float4 &ba,
                                              const float4 &bb, bool both_convex, double thr,
-                                             int union_mode, bool &used64)
+                                             int union_mode, bool &used64, float *scratch)
 {
     if (!both_convex) {
         used64 = true;
@@ -150,7 +151,7 @@ __device__ __forceinline__ bool decide_exact(const Quad &A, const Quad &B, const
         a[2 * k] = A.c[2 * k] - ox; a[2 * k + 1] = A.c[2 * k + 1] - oy;
         b[2 * k] = B.c[2 * k] - ox; b[2 * k + 1] = B.c[2 * k + 1] - oy;
     }
-    FastRes r = fast_quad_pair(a, b);
+    FastRes r = fast_quad_pair_s<S>(a, b, scratch);
     const float t = (float)thr;
     const float margin = r.inter * (1.f + t) - t * (r.area_a + r.area_b);
     const float band = 4.f * r.err + 1e-6f * (r.area_a + r.area_b);
@@ -203,11 +204,12 @@ __device__ __forceinline__ bool frame_prune(const float *p, const float *q, floa
     return (ou * ov) < 0.998f * kthr_sum * l2;                   // inter <= ou*ov/l2 < thr/(1+thr) * (A+B)
 }
 
-__global__ void __launch_bounds__(kSweepWarps * 32)
+__global__ void __launch_bounds__(kSweepWarps * 32, 6)
 nms_sweep_kernel(SweepParams P)
 {
     __shared__ int32_t q1[kSweepWarps][64];    // AABB + area-bound survivors
     __shared__ int32_t q2[kSweepWarps][64];    // projection-bound survivors: these get clipped
+    float scratch[40];                          // clip rings: thread-local (L1-resident) measured faster than a 40 KB shared slab
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nv = *P.nvalid;
     const int nwarps = gridDim.x * kSweepWarps;
@@ -294,7 +296,7 @@ nms_sweep_kernel(SweepParams P)
                         const float4 bb = P.aabb[kk];
                         bool used64;
                         ++c_clip;
-                        edge = decide_exact(A, B, ba, bb, area_i >= 0.f && P.area[kk] >= 0.f, P.thr, P.union_mode, used64);
+                        edge = decide_exact<1>(A, B, ba, bb, area_i >= 0.f && P.area[kk] >= 0.f, P.thr, P.union_mode, used64, scratch);
                         c_64 += used64;
                         const int rk_j = P.rk[kk];
                         lo = rk_i > rk_j ? rk_i : rk_j;   // worse-ranked box is the one suppressed
@@ -334,7 +336,7 @@ nms_sweep_kernel(SweepParams P)
                         const float4 bb = P.aabb[kk];
                         bool used64;
                         ++c_clip;
-                        edge = decide_exact(A, B, ba, bb, area_i >= 0.f && P.area[kk] >= 0.f, P.thr, P.union_mode, used64);
+                        edge = decide_exact<1>(A, B, ba, bb, area_i >= 0.f && P.area[kk] >= 0.f, P.thr, P.union_mode, used64, scratch);
                         c_64 += used64;
                         const int rk_j = P.rk[kk];
                         lo = rk_i > rk_j ? rk_i : rk_j;

@@ -225,7 +225,9 @@ def run_nms(args, rank, world, local, dense=True):
                 "h2d_bytes_per_step": int(dets_h.nbytes), "d2h_bytes_per_step": int(kept * 8 + 4),
                 "api": "DOTA_devkit.poly_nms_gpu.poly_gpu_nms(np.float32[N,9], thr) -> list"},
         "roofline": {"bound": "hbm", "kernel": "nms_sweep_kernel", "achieved": ach, "peak": pk["hbm_gbs"],
-                     "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                     "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                     "traffic": (75025408 if dense else 97354496) if n == 100000 else None,   # ncu dram read+write of this kernel, profiles/
+                     "peak_source": pk["source"],
                      "algorithmic_bytes_per_launch": nms_algorithmic_bytes(n), "kernel_ms": sweep_avg,
                      "kernel_share_of_step": sweep_avg / (total_ms / args.steps)},
     }

@@ -196,11 +196,23 @@ def run(args, rank, world, local, benchmod):
         "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "tiles/s", "h2d_bytes_per_step": int(img_host.nbytes),
                 "d2h_bytes_per_step": int(d2h), "api": "OrientedRepPointsDetector.simple_test(img) -> rbbox2result lists"},
     }
+    traffic = None
+    try:
+        import json as _json
+        import os as _os
+        tj = _json.load(open(_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "profiles",
+                                           "r1_conv_tc_traffic_b8.json")))
+        if depth == 50 and batch == tj["tiles"]:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]      # ncu, all conv launches of one step (cold L2 per launch)
+    except Exception:
+        pass
     if precision == "bf16" and tc_ms > 0:
         ach = tc_flops / (tc_ms * 1e-3) / 1e12
         line["roofline"] = {"bound": "tensor", "kernel": "conv_tc_kernel (all %d launches per step)" % (tc_launches // args.steps),
                             "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                            "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
+                            "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic,
+                            "traffic_note": "dram bytes read+written by the same launches under ncu (profiles/r1_conv_tc_traffic_b8.json)",
+                            "peak_source": pk["source"] + " (sustained)",
                             "algorithmic_flops_per_step": tc_flops / args.steps, "kernel_ms_per_step": tc_ms / args.steps,
                             "kernel_share_of_step": (tc_ms / args.steps) / ms_step,
                             "whole_step_tflops": batch * fl_tile / (ms_step * 1e-3) / 1e12}

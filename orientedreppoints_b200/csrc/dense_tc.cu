@@ -60,6 +60,8 @@ struct alignas(64) TcParams {
     CUtensorMap tmRes[kMaxProb];              // bf16 residual tensors, same boxes
     Problem prob[kMaxProb];
     int tma_epi, epi_bufs;                    // TMA epilogue on/off; output staging buffers (1 or 2)
+    int b_resident;                           // short-K layers: the whole weight slab of this CTA's N tile stays in shared memory
+    int res_bufs;                             // residual landing buffers (2 or 4): prefetch distance res_bufs - 1 passes
     int gn_fused;                             // GroupNorm statistics accumulated in the TMA epilogue (Cout == 256)
     int stem;                                 // producers build conv1's 7x7/2 im2col rows from the NCHW fp32 image
     int nprob, num_m_tiles, n_tiles_n, num_tiles;
@@ -143,6 +145,21 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr)
     d |= (uint64_t)2 << 61;
     return d;
 }
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+template <int ID, int N>
+__device__ __forceinline__ void named_bar()
+{
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 {
     asm volatile(
@@ -155,6 +172,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// split form: issue the load, do independent work, then tmem_ld_wait() before touching the registers
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32])
+{
+    // the registers are tied to the wait so that no use can be scheduled above it
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
 }
 
 // epilogue activation: 0 none, 1 ReLU, 2 exact (erf) GELU as nn.GELU (swin_transformer.py:24-29)
@@ -192,20 +233,31 @@ __device__ __forceinline__ void decode_tile(const TcParams &P, int tile, int &pi
 // BN: accumulator width (32..256).  OUT_F32: fp32 output (head predictions) instead of bf16.
 // DEFORM: A operand produced by warps 6-9 (bilinear gather) instead of TMA.
 template <int BN, bool OUT_F32, bool DEFORM>
-__global__ void __launch_bounds__(DEFORM ? 448 : 192, 1)
+__global__ void __launch_bounds__(DEFORM ? 448 : 352, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
 {
+    // warp roles.  plain: 0 TMA | 1 MMA | 2-9 epilogue (two warps per TMEM lane quarter, splitting the columns) |
+    // 10 residual loader.   deformable / stem: 0 TMA(B) | 1 MMA | 2-5 epilogue | 6-13 A-operand producers.
+    constexpr int kEpiWarps = DEFORM ? 4 : 8;
+    constexpr int kEpiThreads = kEpiWarps * 32;
+    constexpr int kWG = kEpiWarps / 4;                 // epilogue warps per lane quarter
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic: [stages][A 16K | B BN*128]  then the epilogue staging tile [128 rows][HC*2 + 16 B]
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kBBytes = BN * kBK * 2;
-    constexpr int kStageBytes = kABytes + kBBytes;
+    // b_resident: [B slab: kblocks x kBBytes] then A-only stages; otherwise every stage carries A | B
+    const int kStageBytes = P.b_resident ? kABytes : kABytes + kBBytes;
+    const int kblocks_all = P.KH * P.KW * P.cin_blocks;
+    uint8_t *bres = smem;
+    if (P.b_resident) smem += (size_t)kblocks_all * kBBytes;
     constexpr int HC = BN < 64 ? BN : 64;              // columns staged per epilogue pass
     constexpr int kPitch = HC * 2 + 16;                // bytes per staged row (+16: conflict-free 16-byte accesses)
     uint8_t *stage_out = smem + (size_t)stages * kStageBytes;
     __shared__ uint64_t bars[2 * kStagesMax + 4];
     __shared__ float s_bias[256];
-    __shared__ uint64_t res_bar[2];              // residual tile landed (TMA epilogue)
+    __shared__ uint64_t bres_bar;                // resident weight slab landed
+    __shared__ uint64_t res_bar[4];              // residual pass tile landed (TMA epilogue; up to 4 buffers in flight)
+    __shared__ uint64_t res_empty[4];            // residual buffer consumed by the four epilogue warps
     __shared__ uint32_t tmem_slot_s;
     uint64_t *full = bars;                       // [stages]  TMA bytes landed (+ producer arrivals when DEFORM)
     uint64_t *empty = bars + kStagesMax;         // [stages]  MMA finished reading the stage
@@ -228,7 +280,9 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 mbar_init(&full[s], DEFORM ? 1 + 256 : 1);
                 mbar_init(&empty[s], 1);
             }
-            for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); mbar_init(&res_bar[a], 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
+            for (int a = 0; a < 4; ++a) { mbar_init(&res_bar[a], 1); mbar_init(&res_empty[a], kEpiWarps); }
+            mbar_init(&bres_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -245,6 +299,13 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
         // ===================================================== TMA producer
         if (elect_one()) {
             Ring r(stages);
+            if (P.b_resident && (int)blockIdx.x < P.num_tiles) {
+                // gridDim.x is a multiple of n_tiles_n, so every tile of this CTA has the same N tile
+                const int nt0 = blockIdx.x % P.n_tiles_n;
+                mbar_expect_tx(&bres_bar, (uint32_t)(kblocks_all * kBBytes));
+                for (int kb = 0; kb < kblocks_all; ++kb)
+                    tma_load_2d(bres + (size_t)kb * kBBytes, &P.tmB, &bres_bar, kb * kBK, nt0 * BN);
+            }
             for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
                 int pi, wb, hb, ib, nt;
                 decode_tile(P, tile, pi, wb, hb, ib, nt);
@@ -255,9 +316,9 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                     for (int cb = 0; cb < P.cin_blocks; ++cb) {
                         mbar_wait(&empty[r.stage], r.phase ^ 1);
                         uint8_t *sa = smem + (size_t)r.stage * kStageBytes;
-                        mbar_expect_tx(&full[r.stage], DEFORM ? kBBytes : kABytes + kBBytes);
+                        mbar_expect_tx(&full[r.stage], DEFORM ? kBBytes : (P.b_resident ? kABytes : kABytes + kBBytes));
                         if (!DEFORM) tma_load_4d(sa, &P.tmA[pi], &full[r.stage], cb * kBK, w0 + kw, h0 + kh, i0);
-                        tma_load_2d(sa + kABytes, &P.tmB, &full[r.stage], (tap * P.cin_blocks + cb) * kBK, nt * BN);
+                        if (!P.b_resident) tma_load_2d(sa + kABytes, &P.tmB, &full[r.stage], (tap * P.cin_blocks + cb) * kBK, nt * BN);
                         r.next();
                     }
                 }
@@ -269,6 +330,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
         Ring r(stages);
         int acc = 0;
         uint32_t acc_phase = 0;
+        if (P.b_resident && (int)blockIdx.x < P.num_tiles) mbar_wait(&bres_bar, 0);
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
             mbar_wait(&tempty[acc], acc_phase ^ 1);
             tcgen05_fence_after();
@@ -278,7 +340,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 tcgen05_fence_after();
                 if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + (size_t)r.stage * kStageBytes);
-                    const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sa + kABytes);
+                    const uint64_t da = make_desc_sw128(sa);
+                    const uint64_t db = make_desc_sw128(P.b_resident ? smem_u32(bres + (size_t)kb * kBBytes) : sa + kABytes);
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k)
                         umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
@@ -290,11 +353,13 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-    } else if (warp < 6) {
+    } else if (warp < 2 + kEpiWarps) {
         // ===================================================== epilogue (TMEM lane quarter = warp % 4)
         const int q = warp & 3;
-        const int et = threadIdx.x - 64;                   // 0..127 within the epilogue warps
-        int tma_g = 0;                                     // passes issued so far through the TMA epilogue
+        const int wg = (warp - 2) >> 2;                    // which 32-column slice of a 64-column pass this warp owns
+        const int et = threadIdx.x - 64;                   // 0..kEpiThreads-1 within the epilogue warps
+        int ob = 0, rb = 0;                                // staging / residual ring positions (TMA epilogue)
+        uint32_t rb_phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
@@ -315,7 +380,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 mbar_wait(&tfull[acc], acc_phase);
                 tcgen05_fence_after();
 #pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ++ch) {
+                for (int ch = wg; ch < BN / 32; ch += kWG) {
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), v);
                     const int c0 = nt * BN + ch * 32;
@@ -334,86 +399,77 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                     }
                 }
             } else if (P.tma_epi) {
-                // bf16 outputs through the TMA unit: 64-channel passes; the residual pass tile is prefetched by
-                // TMA (128-byte swizzle) one pass ahead, results are written to a swizzled staging tile and
-                // stored with cp.async.bulk.tensor (coalescing and partial-tile clipping done by hardware)
-                uint8_t *Obuf = stage_out;                               // [epi_bufs][16 KiB]
-                uint8_t *Rbuf = stage_out + (size_t)P.epi_bufs * 16384;  // [2][16 KiB]
+                // bf16 outputs through the TMA unit, in 64-channel passes.  The residual pass tile is brought in by
+                // the loader warp (TMA, 128-byte swizzle) up to res_bufs passes ahead; results go to a swizzled
+                // staging tile and leave with cp.async.bulk.tensor (coalescing and partial-tile clipping by hardware).
+                // With eight epilogue warps each warp owns one 32-column half of the pass.
+                const uint32_t obuf_u = smem_u32(stage_out);                                   // [epi_bufs][16 KiB]
+                const uint32_t rbuf_u = obuf_u + (uint32_t)P.epi_bufs * 16384u;                // [res_bufs][16 KiB]
+                const uint32_t bias_u = smem_u32(s_bias);
                 const bool io = (et == 0);
+                const bool has_res = pr.res != nullptr;
                 constexpr int kPasses = BN / 64;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int c = et; c < BN; c += 128) s_bias[c] = (P.bias && nt * BN + c < P.Cout) ? P.bias[nt * BN + c] : 0.f;
-                if (io && pr.res && tma_g == 0) {                         // prologue: residual of the very first pass
-                    mbar_expect_tx(&res_bar[0], 16384);
-                    tma_load_4d(Rbuf, &P.tmRes[pi], &res_bar[0], nt * BN, wb * pr.BW, hb * pr.BH, ib * pr.BI);
-                }
+                named_bar<1, kEpiThreads>();                             // previous tile's bias reads are done
+                for (int c = et; c < BN; c += kEpiThreads) s_bias[c] = (P.bias && nt * BN + c < P.Cout) ? P.bias[nt * BN + c] : 0.f;
 #pragma unroll 1
-                for (int half = 0; half < kPasses; ++half, ++tma_g) {
-                    const int ob = tma_g % P.epi_bufs, rb = tma_g & 1;
+                for (int half = 0; half < kPasses; ++half) {
                     if (io) {
                         if (P.epi_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        // prefetch the residual of the NEXT pass (possibly of the next tile) into the other buffer
-                        int npi = pi, nwb = wb, nhb = hb, nib = ib, nnt = nt, nhalf = half + 1;
-                        bool have_next = true;
-                        if (nhalf == kPasses) {
-                            nhalf = 0;
-                            const int ntile = tile + gridDim.x;
-                            have_next = ntile < P.num_tiles;
-                            if (have_next) decode_tile(P, ntile, npi, nwb, nhb, nib, nnt);
-                        }
-                        if (have_next && P.prob[npi].res) {
-                            const Problem &np = P.prob[npi];
-                            mbar_expect_tx(&res_bar[rb ^ 1], 16384);
-                            tma_load_4d(Rbuf + (size_t)(rb ^ 1) * 16384, &P.tmRes[npi], &res_bar[rb ^ 1], nnt * BN + nhalf * 64,
-                                        nwb * np.BW, nhb * np.BH, nib * np.BI);
-                        }
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");       // staging buffer `ob` is free, bias staged
+                    named_bar<1, kEpiThreads>();                         // staging buffer `ob` is free, bias staged
                     if (half == 0) {
                         mbar_wait(&tfull[acc], acc_phase);
                         tcgen05_fence_after();
                     }
-                    if (pr.res) mbar_wait(&res_bar[rb], (uint32_t)((tma_g >> 1) & 1));
                     float gn_s = 0.f, gn_q = 0.f;
-                    uint8_t *orow = Obuf + (size_t)ob * 16384 + (size_t)rrow * 128;
-                    const uint8_t *rrow_p = Rbuf + (size_t)rb * 16384 + (size_t)rrow * 128;
-#pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
+                    const uint32_t orow = obuf_u + (uint32_t)ob * 16384u + (uint32_t)rrow * 128u;
+                    const uint32_t rrow_u = rbuf_u + (uint32_t)rb * 16384u + (uint32_t)rrow * 128u;
+#pragma unroll 1
+                    for (int ch = wg; ch < 2; ch += kWG) {
                         uint32_t v[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * 64 + ch * 32), v);
+                        tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * 64 + ch * 32), v);
+                        uint4 ru[4];
+                        if (has_res) {
+                            if (ch == wg) mbar_wait(&res_bar[rb], rb_phase);
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) ru[j4] = lds128(rrow_u + ((uint32_t)((ch * 4 + j4) ^ (rrow & 7)) << 4));
+                        }
+                        tmem_ld_wait(v);
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
                             const int c16 = ch * 4 + j4;                  // 16-byte chunk inside the 128-byte row
-                            const int sw = (c16 ^ (rrow & 7)) << 4;
+                            const uint32_t sw = (uint32_t)(c16 ^ (rrow & 7)) << 4;
                             float f[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j4 * 8 + j]);
-                            const float4 b0 = *reinterpret_cast<const float4 *>(&s_bias[half * 64 + c16 * 8]);
-                            const float4 b1 = *reinterpret_cast<const float4 *>(&s_bias[half * 64 + c16 * 8 + 4]);
-                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                            if (pr.res) {
-                                const uint4 u = *reinterpret_cast<const uint4 *>(rrow_p + sw);
-                                const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+                            const uint4 b0 = lds128(bias_u + (uint32_t)(half * 64 + c16 * 8) * 4u);
+                            const uint4 b1 = lds128(bias_u + (uint32_t)(half * 64 + c16 * 8 + 4) * 4u);
+                            f[0] += __uint_as_float(b0.x); f[1] += __uint_as_float(b0.y);
+                            f[2] += __uint_as_float(b0.z); f[3] += __uint_as_float(b0.w);
+                            f[4] += __uint_as_float(b1.x); f[5] += __uint_as_float(b1.y);
+                            f[6] += __uint_as_float(b1.z); f[7] += __uint_as_float(b1.w);
+                            if (has_res) {
+                                const uint32_t uu[4] = {ru[j4].x, ru[j4].y, ru[j4].z, ru[j4].w};
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    const float2 r2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&uu[k]));
-                                    f[2 * k] += r2.x;
-                                    f[2 * k + 1] += r2.y;
+                                    f[2 * k] += __uint_as_float(uu[k] << 16);
+                                    f[2 * k + 1] += __uint_as_float(uu[k] & 0xffff0000u);
                                 }
                             }
-                            if (P.relu) {
+                            if (P.relu == 2) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) f[j] = act_fn(f[j], P.relu);
+                                for (int j = 0; j < 8; ++j) f[j] = act_fn(f[j], 2);
                             }
                             uint32_t pk[4];
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                                // ReLU after rounding: rounding is monotone and keeps the sign, so the result is the same
+                                if (P.relu == 1) b2 = __hmax2(b2, __floats2bfloat162_rn(0.f, 0.f));
                                 pk[k] = *reinterpret_cast<uint32_t *>(&b2);
                             }
-                            *reinterpret_cast<uint4 *>(orow + sw) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            sts128(orow + sw, make_uint4(pk[0], pk[1], pk[2], pk[3]));
                             if (P.gn_fused) {
                                 // one 16-byte chunk = 8 channels = one GroupNorm group (Cout 256 / 32 groups)
                                 float gs = 0.f, gq = 0.f;
@@ -430,7 +486,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             }
                         }
                     }
-                    if (P.gn_fused && lane < 8) {
+                    if (P.gn_fused && lane < 8 && (kWG == 1 || (lane >> 2) == wg)) {
                         // the 32 rows of a warp belong to one image (host guarantees BW*BH >= 32)
                         const int n_img = ib * pr.BI + ((q * 32) >> (pr.lbw + pr.lbh));
                         if (n_img < pr.N) {
@@ -439,29 +495,35 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             atomicAdd(st + 1, (double)gn_q);
                         }
                     }
+                    if (has_res) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&res_empty[rb]);          // this warp is done with residual buffer rb
+                        if (++rb == P.res_bufs) { rb = 0; rb_phase ^= 1; }
+                    }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("bar.sync 3, 128;" ::: "memory");       // staging written by all, residual buffer consumed by all
+                    named_bar<3, kEpiThreads>();                         // staging written by all
                     if (io) {
                         asm volatile(
                             "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                            ::"l"(&P.tmOut[pi]), "r"(smem_u32(Obuf + (size_t)ob * 16384)), "r"(nt * BN + half * 64),
+                            ::"l"(&P.tmOut[pi]), "r"(obuf_u + (uint32_t)ob * 16384u), "r"(nt * BN + half * 64),
                               "r"(wb * pr.BW), "r"(hb * pr.BH), "r"(ib * pr.BI) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
+                    if (++ob == P.epi_bufs) ob = 0;
                 }
             } else {
                 // bf16 outputs: residual tile prefetched into shared memory with coalesced cp.async while the
                 // MMA is still running, results written back to the same staging tile, then stored coalesced
                 const bool vec_ok = (P.Cout & 7) == 0;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int c = et; c < BN; c += 128) s_bias[c] = (P.bias && nt * BN + c < P.Cout) ? P.bias[nt * BN + c] : 0.f;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                named_bar<1, kEpiThreads>();
+                for (int c = et; c < BN; c += kEpiThreads) s_bias[c] = (P.bias && nt * BN + c < P.Cout) ? P.bias[nt * BN + c] : 0.f;
+                named_bar<1, kEpiThreads>();
 #pragma unroll 1
                 for (int half = 0; half < BN / HC; ++half) {
                     const int cbase = nt * BN + half * HC;           // first output channel of this pass
                     constexpr int kChunksPerRow = HC / 8;            // 16-byte chunks per staged row
                     if (pr.res && vec_ok) {
-                        for (int c = et; c < 128 * kChunksPerRow; c += 128) {
+                        for (int c = et; c < 128 * kChunksPerRow; c += kEpiThreads) {
                             const int r = c / kChunksPerRow, k16 = c - r * kChunksPerRow;
                             size_t rp;
                             const bool ok = row_pixel(r, rp) && (cbase + k16 * 8 < P.Cout);
@@ -479,10 +541,10 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                     }
                     if (pr.res && vec_ok) {
                         asm volatile("cp.async.wait_group 0;" ::: "memory");
-                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        named_bar<1, kEpiThreads>();
                     }
 #pragma unroll 1
-                    for (int ch = 0; ch < HC / 32; ++ch) {
+                    for (int ch = wg; ch < HC / 32; ch += kWG) {
                         uint32_t v[32];
                         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HC + ch * 32), v);
                         const int c0 = cbase + ch * 32;
@@ -525,9 +587,9 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             sp[j4] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    named_bar<1, kEpiThreads>();
                     // coalesced copy-out: 16 threads cover one 256-byte row segment
-                    for (int c = et; c < 128 * kChunksPerRow; c += 128) {
+                    for (int c = et; c < 128 * kChunksPerRow; c += kEpiThreads) {
                         const int r = c / kChunksPerRow, k16 = c - r * kChunksPerRow;
                         size_t rp;
                         if (row_pixel(r, rp) && (cbase + k16 * 8 < P.Cout)) {
@@ -541,7 +603,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             }
                         }
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    named_bar<1, kEpiThreads>();
                 }
             }
             tcgen05_fence_before();
@@ -550,6 +612,29 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (P.tma_epi && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores drained before exit
+    } else if (!DEFORM) {
+        // ===================================================== residual loader (warp 10 of the plain kernel)
+        // One thread streams the 64-channel residual pass tiles of this CTA's tiles into the ring of landing buffers,
+        // as far ahead as free buffers allow - off the epilogue's critical path.
+        if (P.tma_epi && warp == 2 + kEpiWarps && elect_one()) {
+            constexpr int kPasses = BN / 64 > 0 ? BN / 64 : 1;
+            uint8_t *Rbuf = stage_out + (size_t)P.epi_bufs * 16384;
+            int rb = 0;
+            uint32_t rb_phase = 0;
+            for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+                int pi, wb, hb, ib, nt;
+                decode_tile(P, tile, pi, wb, hb, ib, nt);
+                const Problem &pr = P.prob[pi];
+                if (!pr.res) continue;
+                for (int half = 0; half < kPasses; ++half) {
+                    mbar_wait(&res_empty[rb], rb_phase ^ 1);
+                    mbar_expect_tx(&res_bar[rb], 16384);
+                    tma_load_4d(Rbuf + (size_t)rb * 16384, &P.tmRes[pi], &res_bar[rb], nt * BN + half * 64, wb * pr.BW, hb * pr.BH,
+                                ib * pr.BI);
+                    if (++rb == P.res_bufs) { rb = 0; rb_phase ^= 1; }
+                }
+            }
+        }
     } else if (DEFORM) {
         // ===================================================== deformable A-operand producers (warps 6-13)
         // Per tap: threads 0-127 compute the bilinear parameters of their output pixel (4 weights + 4 element
@@ -756,7 +841,7 @@ thread_local TcTrace g_tc_trace[kEvPool];
 template <int BN, bool OUT_F32, bool DEFORM>
 int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st, int staging_bytes)
 {
-    const size_t smem = 1024 + (size_t)stages * (kABytes + BN * kBK * 2) + (size_t)staging_bytes;
+    const size_t smem = 1024 + (size_t)stages * (P.b_resident ? kABytes : kABytes + BN * kBK * 2) + (size_t)staging_bytes;
     auto kern = conv_tc_kernel<BN, OUT_F32, DEFORM>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -781,7 +866,7 @@ int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st, int stag
         g_tc_trace[slot] = TcTrace{P.nprob, P.prob[0].N, P.prob[0].H, P.prob[0].W, P.Cin, P.Cout, P.KH, P.stride, DEFORM ? 1 : 0,
                                    BN, P.num_tiles, grid, fl};
     }
-    kern<<<grid, DEFORM ? 448 : 192, smem, st>>>(P, stages);
+    kern<<<grid, DEFORM ? 448 : 352, smem, st>>>(P, stages);
     ORP_LAUNCHED();
     if (slot >= 0) ORP_CUDA(cudaEventRecord(g_tc_ev[slot][1], st));
     return ORP_OK;
@@ -929,6 +1014,9 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     P.gn_fused = (want_gn && gn_ok) ? 1 : 0;
     const bool mem_bound = any_res || (KH * KW * (Cin / kBK) <= 8);
     P.epi_bufs = mem_bound ? 2 : 1;
+    P.res_bufs = 2;
+    // short-K layers (<= 2 K blocks): keep this CTA's weight slab resident, stages carry only the A tile
+    P.b_resident = (!deform && KH * KW * P.cin_blocks <= 2 && !getenv("ORP_TC_NO_BRES")) ? 1 : 0;
     if (P.tma_epi) {
         for (int i = 0; i < nprob; ++i) {
             const Problem &pr = P.prob[i];
@@ -954,12 +1042,15 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
         ORP_CUDA(cudaGetDevice(&dev));
         ORP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    const int grid = P.num_tiles < sms ? P.num_tiles : sms;
-    const int stage_bytes = kABytes + BN * kBK * 2;
+    int grid = P.num_tiles < sms ? P.num_tiles : sms;
+    if (P.b_resident && grid >= P.n_tiles_n) grid -= grid % P.n_tiles_n;       // fixed N tile per CTA
+    else if (P.b_resident) P.b_resident = 0;
+    const int stage_bytes = P.b_resident ? kABytes : kABytes + BN * kBK * 2;
+    const int bres_bytes = P.b_resident ? KH * KW * P.cin_blocks * BN * kBK * 2 : 0;
     const int hc = BN < 64 ? BN : 64;
     int staging = out_f32 ? 0 : 128 * (hc * 2 + 16);
-    if (P.tma_epi) staging = (P.epi_bufs + (any_res ? 2 : 0)) * 16384;
-    int stages = (int)((227 * 1024 - 4096 - 1024 - staging) / stage_bytes);
+    if (P.tma_epi) staging = (P.epi_bufs + (any_res ? P.res_bufs : 0)) * 16384;
+    int stages = (int)((227 * 1024 - 4096 - 1024 - staging - bres_bytes) / stage_bytes);
     if (stages > kStagesMax) stages = kStagesMax;
     if (deform && stages > 3) stages = 3;     // leave L1 capacity for the bilinear gather (corner reuse between neighbouring pixels)
     int lrc = ORP_EINVAL;
@@ -967,8 +1058,8 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
 #define ORP_TC_DISPATCH(BNV)                                                                     \
     if (!launched && BN == BNV) {                                                                \
         launched = true;                                                                         \
-        if (deform) lrc = out_f32 ? launch_tc<BNV, true, true>(P, stages, grid, st, staging) : launch_tc<BNV, false, true>(P, stages, grid, st, staging); \
-        else lrc = out_f32 ? launch_tc<BNV, true, false>(P, stages, grid, st, staging) : launch_tc<BNV, false, false>(P, stages, grid, st, staging);       \
+        if (deform) lrc = out_f32 ? launch_tc<BNV, true, true>(P, stages, grid, st, staging + bres_bytes) : launch_tc<BNV, false, true>(P, stages, grid, st, staging + bres_bytes); \
+        else lrc = out_f32 ? launch_tc<BNV, true, false>(P, stages, grid, st, staging + bres_bytes) : launch_tc<BNV, false, false>(P, stages, grid, st, staging + bres_bytes);       \
     }
     ORP_TC_DISPATCH(256)
     ORP_TC_DISPATCH(128)

@@ -58,10 +58,11 @@ struct alignas(64) TcParams {
     CUtensorMap tmB;
     CUtensorMap tmOut[kMaxProb];              // bf16 output tensors, box {64 ch, BW, BH, BI} (TMA-store epilogue)
     CUtensorMap tmRes[kMaxProb];              // bf16 residual tensors, same boxes
+    CUtensorMap tmI;                          // 64 x 64 bf16 identity (residual add on the tensor core)
     Problem prob[kMaxProb];
     int tma_epi, epi_bufs;                    // TMA epilogue on/off; output staging buffers (1 or 2)
     int b_resident;                           // short-K layers: the whole weight slab of this CTA's N tile stays in shared memory
-    int res_bufs;                             // residual landing buffers (2 or 4): prefetch distance res_bufs - 1 passes
+    int res_mma;                              // residual added by the tensor core: extra K blocks  R[128x64] * I[64x64]
     int gn_fused;                             // GroupNorm statistics accumulated in the TMA epilogue (Cout == 256)
     int stem;                                 // producers build conv1's 7x7/2 im2col rows from the NCHW fp32 image
     int nprob, num_m_tiles, n_tiles_n, num_tiles;
@@ -229,15 +230,25 @@ __device__ __forceinline__ void decode_tile(const TcParams &P, int tile, int &pi
     ib = local / (pr.tiles_w * pr.tiles_h);
 }
 
+// 64 x 64 bf16 identity, the B operand that adds a residual tile into the accumulator
+struct IdentBlock { unsigned short v[64 * 64]; };
+constexpr IdentBlock make_ident()
+{
+    IdentBlock b{};
+    for (int i = 0; i < 64; ++i) b.v[i * 64 + i] = 0x3F80;   // bf16 1.0
+    return b;
+}
+__device__ IdentBlock g_ident = make_ident();
+
 // ----------------------------------------------------------------------------------------------- kernel
 // BN: accumulator width (32..256).  OUT_F32: fp32 output (head predictions) instead of bf16.
 // DEFORM: A operand produced by warps 6-9 (bilinear gather) instead of TMA.
 template <int BN, bool OUT_F32, bool DEFORM>
-__global__ void __launch_bounds__(DEFORM ? 448 : 352, 1)
+__global__ void __launch_bounds__(DEFORM ? 448 : 320, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
 {
-    // warp roles.  plain: 0 TMA | 1 MMA | 2-9 epilogue (two warps per TMEM lane quarter, splitting the columns) |
-    // 10 residual loader.   deformable / stem: 0 TMA(B) | 1 MMA | 2-5 epilogue | 6-13 A-operand producers.
+    // warp roles.  plain: 0 TMA | 1 MMA | 2-9 epilogue (two warps per TMEM lane quarter, splitting the columns).
+    // deformable / stem: 0 TMA(B) | 1 MMA | 2-5 epilogue | 6-13 A-operand producers.
     constexpr int kEpiWarps = DEFORM ? 4 : 8;
     constexpr int kEpiThreads = kEpiWarps * 32;
     constexpr int kWG = kEpiWarps / 4;                 // epilogue warps per lane quarter
@@ -248,6 +259,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     // b_resident: [B slab: kblocks x kBBytes] then A-only stages; otherwise every stage carries A | B
     const int kStageBytes = P.b_resident ? kABytes : kABytes + kBBytes;
     const int kblocks_all = P.KH * P.KW * P.cin_blocks;
+    uint8_t *ident = smem;                             // [8 KiB] identity block when res_mma
+    if (P.res_mma) smem += 8192;
     uint8_t *bres = smem;
     if (P.b_resident) smem += (size_t)kblocks_all * kBBytes;
     constexpr int HC = BN < 64 ? BN : 64;              // columns staged per epilogue pass
@@ -256,8 +269,6 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     __shared__ uint64_t bars[2 * kStagesMax + 4];
     __shared__ float s_bias[256];
     __shared__ uint64_t bres_bar;                // resident weight slab landed
-    __shared__ uint64_t res_bar[4];              // residual pass tile landed (TMA epilogue; up to 4 buffers in flight)
-    __shared__ uint64_t res_empty[4];            // residual buffer consumed by the four epilogue warps
     __shared__ uint32_t tmem_slot_s;
     uint64_t *full = bars;                       // [stages]  TMA bytes landed (+ producer arrivals when DEFORM)
     uint64_t *empty = bars + kStagesMax;         // [stages]  MMA finished reading the stage
@@ -281,7 +292,6 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 mbar_init(&empty[s], 1);
             }
             for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
-            for (int a = 0; a < 4; ++a) { mbar_init(&res_bar[a], 1); mbar_init(&res_empty[a], kEpiWarps); }
             mbar_init(&bres_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -299,12 +309,14 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
         // ===================================================== TMA producer
         if (elect_one()) {
             Ring r(stages);
-            if (P.b_resident && (int)blockIdx.x < P.num_tiles) {
+            if ((P.b_resident || P.res_mma) && (int)blockIdx.x < P.num_tiles) {
                 // gridDim.x is a multiple of n_tiles_n, so every tile of this CTA has the same N tile
                 const int nt0 = blockIdx.x % P.n_tiles_n;
-                mbar_expect_tx(&bres_bar, (uint32_t)(kblocks_all * kBBytes));
-                for (int kb = 0; kb < kblocks_all; ++kb)
-                    tma_load_2d(bres + (size_t)kb * kBBytes, &P.tmB, &bres_bar, kb * kBK, nt0 * BN);
+                mbar_expect_tx(&bres_bar, (uint32_t)((P.b_resident ? kblocks_all * kBBytes : 0) + (P.res_mma ? 8192 : 0)));
+                if (P.res_mma) tma_load_2d(ident, &P.tmI, &bres_bar, 0, 0);
+                if (P.b_resident)
+                    for (int kb = 0; kb < kblocks_all; ++kb)
+                        tma_load_2d(bres + (size_t)kb * kBBytes, &P.tmB, &bres_bar, kb * kBK, nt0 * BN);
             }
             for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
                 int pi, wb, hb, ib, nt;
@@ -322,6 +334,16 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                         r.next();
                     }
                 }
+                if (!DEFORM && P.res_mma) {
+                    // residual: one extra K block per 64 output channels, the A operand is the residual tile itself
+                    for (int g = 0; g < BN / 64 && nt * BN + g * 64 < P.Cout; ++g) {
+                        mbar_wait(&empty[r.stage], r.phase ^ 1);
+                        mbar_expect_tx(&full[r.stage], kABytes);
+                        tma_load_4d(smem + (size_t)r.stage * kStageBytes, &P.tmRes[pi], &full[r.stage], nt * BN + g * 64,
+                                    wb * pr.BW, hb * pr.BH, ib * pr.BI);
+                        r.next();
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -330,8 +352,14 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
         Ring r(stages);
         int acc = 0;
         uint32_t acc_phase = 0;
-        if (P.b_resident && (int)blockIdx.x < P.num_tiles) mbar_wait(&bres_bar, 0);
+        constexpr uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        if ((P.b_resident || P.res_mma) && (int)blockIdx.x < P.num_tiles) mbar_wait(&bres_bar, 0);
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+            int res_groups = 0;
+            if (!DEFORM && P.res_mma) {
+                const int nt = tile % P.n_tiles_n;
+                for (int g = 0; g < BN / 64 && nt * BN + g * 64 < P.Cout; ++g) ++res_groups;
+            }
             mbar_wait(&tempty[acc], acc_phase ^ 1);
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -346,7 +374,23 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                     for (int k = 0; k < kBK / 16; ++k)
                         umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
                     umma_commit(&empty[r.stage]);
-                    if (kb == kblocks - 1) umma_commit(&tfull[acc]);
+                    if (kb == kblocks - 1 && res_groups == 0) umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                r.next();
+            }
+            for (int g = 0; g < res_groups; ++g) {
+                // accumulator columns [64 g, 64 g + 64) += residual tile * identity
+                mbar_wait(&full[r.stage], r.phase);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint64_t da = make_desc_sw128(smem_u32(smem + (size_t)r.stage * kStageBytes));
+                    const uint64_t db = make_desc_sw128(smem_u32(ident));
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k)
+                        umma_bf16(d_tmem + (uint32_t)(g * 64), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc64, 1u);
+                    umma_commit(&empty[r.stage]);
+                    if (g == res_groups - 1) umma_commit(&tfull[acc]);
                 }
                 __syncwarp();
                 r.next();
@@ -358,8 +402,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
         const int q = warp & 3;
         const int wg = (warp - 2) >> 2;                    // which 32-column slice of a 64-column pass this warp owns
         const int et = threadIdx.x - 64;                   // 0..kEpiThreads-1 within the epilogue warps
-        int ob = 0, rb = 0;                                // staging / residual ring positions (TMA epilogue)
-        uint32_t rb_phase = 0;
+        int ob = 0;                                        // staging ring position (TMA epilogue)
+        int bias_nt = -1;                                  // N tile whose bias slice is staged in s_bias
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
@@ -399,18 +443,19 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                     }
                 }
             } else if (P.tma_epi) {
-                // bf16 outputs through the TMA unit, in 64-channel passes.  The residual pass tile is brought in by
-                // the loader warp (TMA, 128-byte swizzle) up to res_bufs passes ahead; results go to a swizzled
-                // staging tile and leave with cp.async.bulk.tensor (coalescing and partial-tile clipping by hardware).
+                // bf16 outputs through the TMA unit, in 64-channel passes: results go to a 128-byte-swizzled staging
+                // tile and leave with cp.async.bulk.tensor (coalescing and partial-tile clipping by hardware).  A
+                // residual is already in the accumulator (added by the tensor core, see the MMA warp).
                 // With eight epilogue warps each warp owns one 32-column half of the pass.
                 const uint32_t obuf_u = smem_u32(stage_out);                                   // [epi_bufs][16 KiB]
-                const uint32_t rbuf_u = obuf_u + (uint32_t)P.epi_bufs * 16384u;                // [res_bufs][16 KiB]
                 const uint32_t bias_u = smem_u32(s_bias);
                 const bool io = (et == 0);
-                const bool has_res = pr.res != nullptr;
                 constexpr int kPasses = BN / 64;
-                named_bar<1, kEpiThreads>();                             // previous tile's bias reads are done
-                for (int c = et; c < BN; c += kEpiThreads) s_bias[c] = (P.bias && nt * BN + c < P.Cout) ? P.bias[nt * BN + c] : 0.f;
+                if (nt != bias_nt) {                                     // bias slice changes only with the N tile
+                    named_bar<1, kEpiThreads>();                         // previous tile's bias reads are done
+                    for (int c = et; c < BN; c += kEpiThreads) s_bias[c] = (P.bias && nt * BN + c < P.Cout) ? P.bias[nt * BN + c] : 0.f;
+                    bias_nt = nt;
+                }
 #pragma unroll 1
                 for (int half = 0; half < kPasses; ++half) {
                     if (io) {
@@ -424,17 +469,14 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                     }
                     float gn_s = 0.f, gn_q = 0.f;
                     const uint32_t orow = obuf_u + (uint32_t)ob * 16384u + (uint32_t)rrow * 128u;
-                    const uint32_t rrow_u = rbuf_u + (uint32_t)rb * 16384u + (uint32_t)rrow * 128u;
 #pragma unroll 1
                     for (int ch = wg; ch < 2; ch += kWG) {
                         uint32_t v[32];
                         tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * 64 + ch * 32), v);
-                        uint4 ru[4];
-                        if (has_res) {
-                            if (ch == wg) mbar_wait(&res_bar[rb], rb_phase);
+                        // bias slice of these 32 columns: eight back-to-back shared loads, in flight with the TMEM load
+                        uint4 bu[8];
 #pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) ru[j4] = lds128(rrow_u + ((uint32_t)((ch * 4 + j4) ^ (rrow & 7)) << 4));
-                        }
+                        for (int j8 = 0; j8 < 8; ++j8) bu[j8] = lds128(bias_u + (uint32_t)(half * 64 + ch * 32 + j8 * 4) * 4u);
                         tmem_ld_wait(v);
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
@@ -443,20 +485,11 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             float f[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j4 * 8 + j]);
-                            const uint4 b0 = lds128(bias_u + (uint32_t)(half * 64 + c16 * 8) * 4u);
-                            const uint4 b1 = lds128(bias_u + (uint32_t)(half * 64 + c16 * 8 + 4) * 4u);
+                            const uint4 b0 = bu[2 * j4], b1 = bu[2 * j4 + 1];
                             f[0] += __uint_as_float(b0.x); f[1] += __uint_as_float(b0.y);
                             f[2] += __uint_as_float(b0.z); f[3] += __uint_as_float(b0.w);
                             f[4] += __uint_as_float(b1.x); f[5] += __uint_as_float(b1.y);
                             f[6] += __uint_as_float(b1.z); f[7] += __uint_as_float(b1.w);
-                            if (has_res) {
-                                const uint32_t uu[4] = {ru[j4].x, ru[j4].y, ru[j4].z, ru[j4].w};
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    f[2 * k] += __uint_as_float(uu[k] << 16);
-                                    f[2 * k + 1] += __uint_as_float(uu[k] & 0xffff0000u);
-                                }
-                            }
                             if (P.relu == 2) {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) f[j] = act_fn(f[j], 2);
@@ -494,11 +527,6 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             atomicAdd(st, (double)gn_s);
                             atomicAdd(st + 1, (double)gn_q);
                         }
-                    }
-                    if (has_res) {
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&res_empty[rb]);          // this warp is done with residual buffer rb
-                        if (++rb == P.res_bufs) { rb = 0; rb_phase ^= 1; }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     named_bar<3, kEpiThreads>();                         // staging written by all
@@ -612,29 +640,6 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (P.tma_epi && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores drained before exit
-    } else if (!DEFORM) {
-        // ===================================================== residual loader (warp 10 of the plain kernel)
-        // One thread streams the 64-channel residual pass tiles of this CTA's tiles into the ring of landing buffers,
-        // as far ahead as free buffers allow - off the epilogue's critical path.
-        if (P.tma_epi && warp == 2 + kEpiWarps && elect_one()) {
-            constexpr int kPasses = BN / 64 > 0 ? BN / 64 : 1;
-            uint8_t *Rbuf = stage_out + (size_t)P.epi_bufs * 16384;
-            int rb = 0;
-            uint32_t rb_phase = 0;
-            for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-                int pi, wb, hb, ib, nt;
-                decode_tile(P, tile, pi, wb, hb, ib, nt);
-                const Problem &pr = P.prob[pi];
-                if (!pr.res) continue;
-                for (int half = 0; half < kPasses; ++half) {
-                    mbar_wait(&res_empty[rb], rb_phase ^ 1);
-                    mbar_expect_tx(&res_bar[rb], 16384);
-                    tma_load_4d(Rbuf + (size_t)rb * 16384, &P.tmRes[pi], &res_bar[rb], nt * BN + half * 64, wb * pr.BW, hb * pr.BH,
-                                ib * pr.BI);
-                    if (++rb == P.res_bufs) { rb = 0; rb_phase ^= 1; }
-                }
-            }
-        }
     } else if (DEFORM) {
         // ===================================================== deformable A-operand producers (warps 6-13)
         // Per tap: threads 0-127 compute the bilinear parameters of their output pixel (4 weights + 4 element
@@ -866,7 +871,7 @@ int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st, int stag
         g_tc_trace[slot] = TcTrace{P.nprob, P.prob[0].N, P.prob[0].H, P.prob[0].W, P.Cin, P.Cout, P.KH, P.stride, DEFORM ? 1 : 0,
                                    BN, P.num_tiles, grid, fl};
     }
-    kern<<<grid, DEFORM ? 448 : 352, smem, st>>>(P, stages);
+    kern<<<grid, DEFORM ? 448 : 320, smem, st>>>(P, stages);
     ORP_LAUNCHED();
     if (slot >= 0) ORP_CUDA(cudaEventRecord(g_tc_ev[slot][1], st));
     return ORP_OK;
@@ -1013,10 +1018,26 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     }
     P.gn_fused = (want_gn && gn_ok) ? 1 : 0;
     const bool mem_bound = any_res || (KH * KW * (Cin / kBK) <= 8);
-    P.epi_bufs = mem_bound ? 2 : 1;
-    P.res_bufs = 2;
-    // short-K layers (<= 2 K blocks): keep this CTA's weight slab resident, stages carry only the A tile
-    P.b_resident = (!deform && KH * KW * P.cin_blocks <= 2 && !getenv("ORP_TC_NO_BRES")) ? 1 : 0;
+    P.epi_bufs = mem_bound ? 2 : 1;          // a second staging tile costs compute-bound layers a main-loop stage
+    if (const char *e = getenv("ORP_TC_EPI_BUFS")) P.epi_bufs = atoi(e) == 1 ? 1 : 2;
+    // residual through the tensor core (TMA epilogue only; the staged epilogue adds it itself)
+    P.res_mma = (P.tma_epi && any_res) ? 1 : 0;
+    if (P.res_mma) {
+        if (deform) return fail(ORP_EINVAL, "conv2d_bf16: residual is not supported on the deformable path");
+        for (int i = 0; i < nprob; ++i)
+            if (!probs[i].residual_bf16) return fail(ORP_EINVAL, "conv2d_bf16: residual must be given for every problem or none");
+        void *ident_ptr = nullptr;
+        ORP_CUDA(cudaGetSymbolAddress(&ident_ptr, g_ident));
+        cuuint64_t gdim[2] = {64, 64};
+        cuuint64_t gstr[1] = {128};
+        cuuint32_t box[2] = {64, 64};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&P.tmI, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ident_ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_bf16: cuTensorMapEncodeTiled(identity) failed");
+    }
+    // layers whose whole weight slab for one N tile is <= 72 KiB keep it resident; stages then carry only the A tile
+    P.b_resident = (!deform && KH * KW * P.cin_blocks * BN * kBK * 2 <= 72 * 1024 && !getenv("ORP_TC_NO_BRES")) ? 1 : 0;
     if (P.tma_epi) {
         for (int i = 0; i < nprob; ++i) {
             const Problem &pr = P.prob[i];
@@ -1046,10 +1067,10 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     if (P.b_resident && grid >= P.n_tiles_n) grid -= grid % P.n_tiles_n;       // fixed N tile per CTA
     else if (P.b_resident) P.b_resident = 0;
     const int stage_bytes = P.b_resident ? kABytes : kABytes + BN * kBK * 2;
-    const int bres_bytes = P.b_resident ? KH * KW * P.cin_blocks * BN * kBK * 2 : 0;
+    const int bres_bytes = (P.b_resident ? KH * KW * P.cin_blocks * BN * kBK * 2 : 0) + (P.res_mma ? 8192 : 0);
     const int hc = BN < 64 ? BN : 64;
     int staging = out_f32 ? 0 : 128 * (hc * 2 + 16);
-    if (P.tma_epi) staging = (P.epi_bufs + (any_res ? P.res_bufs : 0)) * 16384;
+    if (P.tma_epi) staging = P.epi_bufs * 16384;
     int stages = (int)((227 * 1024 - 4096 - 1024 - staging - bres_bytes) / stage_bytes);
     if (stages > kStagesMax) stages = kStagesMax;
     if (deform && stages > 3) stages = 3;     // leave L1 capacity for the bilinear gather (corner reuse between neighbouring pixels)

@@ -263,6 +263,18 @@ int orp_gn_stats_bf16(const void *x, int N, int HW, int C, int groups, double *s
 int orp_gn_apply_bf16(const void *x, int N, int H, int W, int C, const double *stats, int groups,
                       const float *gamma, const float *beta, float eps, int relu, const void *up_src, void *y,
                       void *stream);
+/* the same for up to 8 tensors that share gamma / beta (the five pyramid levels of one head tower layer,
+ * orientedreppoints_head.py:175-190) in one launch.  up_src (optional, [N,(H+1)/2,(W+1)/2,256]) is added after the
+ * normalisation with nearest-neighbour upsampling (the FPN top-down path, fpn.py:171-176). */
+typedef struct orp_gn_problem {
+    const void *x;        /* bf16 NHWC [N,H,W,256] */
+    int N, H, W;
+    const double *stats;  /* [N,32,2] sums / sums of squares */
+    const void *up_src;   /* optional */
+    void *y;              /* bf16 NHWC [N,H,W,256] */
+} orp_gn_problem;
+int orp_gn_apply_bf16_multi(int nprob, const orp_gn_problem *probs, int C, int groups, const float *gamma,
+                            const float *beta, float eps, int relu, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Swin-T backbone pieces (mmdet/models/backbones/swin_transformer.py); the Linear layers are

@@ -33,6 +33,10 @@ class TcProblem(ctypes.Structure):
                 ("residual_f32", _vp), ("offset", _vp), ("gn_stats", _vp)]
 
 
+class GnProblem(ctypes.Structure):
+    _fields_ = [("x", _vp), ("N", _i), ("H", _i), ("W", _i), ("stats", _vp), ("up_src", _vp), ("y", _vp)]
+
+
 # name -> (restype, argtypes); every symbol include/orp_b200.h declares
 SIGNATURES = {
     "orp_last_error": (ctypes.c_char_p, []),
@@ -68,6 +72,7 @@ SIGNATURES = {
     "orp_maxpool3x3s2_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "orp_gn_stats_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "orp_gn_apply_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _f, _i, _vp, _vp, _vp]),
+    "orp_gn_apply_bf16_multi": (_i, [_i, _vp, _i, _i, _vp, _vp, _f, _i, _vp]),
 }
 
 _LIB = None

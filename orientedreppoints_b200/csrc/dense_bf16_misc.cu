@@ -3,6 +3,7 @@
 // GroupNorm statistics and apply (+ReLU, + the FPN top-down nearest-2x add).  All HBM-bound: 16-byte
 // vector accesses, grids sized in multiples of the SM count.
 #include <cuda_bf16.h>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -130,24 +131,64 @@ gn_stats_bf16_kernel(const __nv_bfloat16 *__restrict__ x, int HW, int slab, doub
     }
 }
 
+struct GnApplyProb {
+    const __nv_bfloat16 *x;
+    const double *stats;
+    const __nv_bfloat16 *up;
+    __nv_bfloat16 *y;
+    int N, H, W;
+    int img_start;                  // first blockIdx.y of this problem
+};
+struct GnApplyParams {
+    GnApplyProb p[8];
+    int nprob;
+    const float *gamma, *beta;
+    float eps;
+    int relu;
+};
+
+// One (problem, image) per blockIdx.y.  A thread always works on the same channel group (its index & 31), so the
+// group's mean / rstd and the eight gamma / beta values live in registers; per 16-byte chunk the work is one load,
+// eight multiply-adds, the optional nearest-neighbour top-down add (fpn.py:171-176) and one store.
 __global__ void __launch_bounds__(256)
-gn_apply_bf16_kernel(const __nv_bfloat16 *__restrict__ x, int N, int H, int W, const double *__restrict__ stats,
-                     const float *__restrict__ gamma, const float *__restrict__ beta, float eps, int relu,
-                     const __nv_bfloat16 *__restrict__ up, __nv_bfloat16 *__restrict__ y)
+gn_apply_bf16_kernel(const __grid_constant__ GnApplyParams P)
 {
-    const size_t total = (size_t)N * H * W * 32;
+    int pi = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k)
+        if (k < P.nprob && (int)blockIdx.y >= P.p[k].img_start) pi = k;
+    const GnApplyProb &pr = P.p[pi];
+    const int n = (int)blockIdx.y - pr.img_start;
+    const int H = pr.H, W = pr.W;
+    const uint32_t chunks = (uint32_t)H * W * 32;           // 16-byte chunks of this image
+    const uint32_t first = blockIdx.x * 2048u + threadIdx.x;
+    if (first >= chunks) return;
+    const int g = threadIdx.x & 31;
     const double cnt = (double)H * W * 8;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int g = (int)(i & 31);
-        const size_t pix = i >> 5;
-        const int n = (int)(pix / ((size_t)H * W));
-        const double sm = stats[((size_t)n * 32 + g) * 2], sq = stats[((size_t)n * 32 + g) * 2 + 1];
-        const double mean = sm / cnt;
-        double var = sq / cnt - mean * mean;
-        var = var < 0 ? 0 : var;
-        const float rstd = (float)(1.0 / sqrt(var + (double)eps)), mu = (float)mean;
-        const uint4 u = reinterpret_cast<const uint4 *>(x)[i];
-        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+    const double sm = pr.stats[((size_t)n * 32 + g) * 2], sq = pr.stats[((size_t)n * 32 + g) * 2 + 1];
+    const double mean = sm / cnt;
+    double var = sq / cnt - mean * mean;
+    var = var < 0 ? 0 : var;
+    const float rstd = (float)(1.0 / sqrt(var + (double)P.eps)), mu = (float)mean;
+    const float4 g0 = *reinterpret_cast<const float4 *>(P.gamma + g * 8), g1 = *reinterpret_cast<const float4 *>(P.gamma + g * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4 *>(P.beta + g * 8), b1 = *reinterpret_cast<const float4 *>(P.beta + g * 8 + 4);
+    const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const uint4 *xi = reinterpret_cast<const uint4 *>(pr.x) + (size_t)n * chunks;
+    uint4 *yi = reinterpret_cast<uint4 *>(pr.y) + (size_t)n * chunks;
+    const int Hu = (H + 1) / 2, Wu = (W + 1) / 2;           // F.interpolate(size=prev_shape, mode='nearest'): src = floor(dst * in / out)
+    const __nv_bfloat16 *upi = pr.up ? pr.up + (size_t)n * Hu * Wu * 256 + g * 8 : nullptr;
+    uint4 u[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const uint32_t i = first + it * 256u;
+        if (i < chunks) u[it] = xi[i];
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const uint32_t i = first + it * 256u;
+        if (i >= chunks) break;
+        const uint32_t uu[4] = {u[it].x, u[it].y, u[it].z, u[it].w};
         float o[8];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -155,20 +196,15 @@ gn_apply_bf16_kernel(const __nv_bfloat16 *__restrict__ x, int N, int H, int W, c
             o[2 * k] = f.x;
             o[2 * k + 1] = f.y;
         }
-        const float4 g0 = *reinterpret_cast<const float4 *>(gamma + g * 8), g1 = *reinterpret_cast<const float4 *>(gamma + g * 8 + 4);
-        const float4 b0 = *reinterpret_cast<const float4 *>(beta + g * 8), b1 = *reinterpret_cast<const float4 *>(beta + g * 8 + 4);
-        const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             o[j] = (o[j] - mu) * rstd * ga[j] + be[j];
-            if (relu) o[j] = fmaxf(o[j], 0.f);
+            if (P.relu) o[j] = fmaxf(o[j], 0.f);
         }
-        if (up) {
-            const int hw = (int)(pix % ((size_t)H * W));
+        if (upi) {
+            const int hw = (int)(i >> 5);
             const int h = hw / W, w = hw - h * W;
-            const int Hu = (H + 1) / 2, Wu = (W + 1) / 2;              // F.interpolate(size=prev_shape, mode='nearest'): src = floor(dst * in / out)
-            const uint4 v = *reinterpret_cast<const uint4 *>(up + (((size_t)n * Hu + (h * Hu) / H) * Wu + (w * Wu) / W) * 256 + g * 8);
+            const uint4 v = *reinterpret_cast<const uint4 *>(upi + ((size_t)((h * Hu) / H) * Wu + (w * Wu) / W) * 256);
             const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -177,7 +213,7 @@ gn_apply_bf16_kernel(const __nv_bfloat16 *__restrict__ x, int N, int H, int W, c
                 o[2 * k + 1] += f.y;
             }
         }
-        reinterpret_cast<uint4 *>(y)[i] = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
+        yi[i] = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
     }
 }
 
@@ -235,17 +271,44 @@ extern "C" int orp_gn_stats_bf16(const void *x, int N, int HW, int C, int groups
     return ORP_OK;
 }
 
+extern "C" int orp_gn_apply_bf16_multi(int nprob, const orp_gn_problem *probs, int C, int groups, const float *gamma,
+                                       const float *beta, float eps, int relu, void *stream)
+{
+    if (nprob < 1 || nprob > 8 || !probs || !gamma || !beta || C != 256 || groups != 32)
+        return fail(ORP_EINVAL, "gn_apply_bf16: needs 1..8 problems, C=256, 32 groups");
+    int rc = ensure_device();
+    if (rc) return rc;
+    GnApplyParams P;
+    memset(&P, 0, sizeof(P));
+    P.nprob = nprob; P.gamma = gamma; P.beta = beta; P.eps = eps; P.relu = relu;
+    int imgs = 0;
+    size_t max_chunks = 0;
+    for (int i = 0; i < nprob; ++i) {
+        const orp_gn_problem &q = probs[i];
+        if (!q.x || !q.y || !q.stats || q.N < 1 || q.H < 1 || q.W < 1) return fail(ORP_EINVAL, "gn_apply_bf16: bad problem");
+        if ((size_t)q.H * q.W * 32 > 0xffffffffull) return fail(ORP_EINVAL, "gn_apply_bf16: image too large");
+        P.p[i].x = static_cast<const __nv_bfloat16 *>(q.x);
+        P.p[i].stats = q.stats;
+        P.p[i].up = static_cast<const __nv_bfloat16 *>(q.up_src);
+        P.p[i].y = static_cast<__nv_bfloat16 *>(q.y);
+        P.p[i].N = q.N; P.p[i].H = q.H; P.p[i].W = q.W;
+        P.p[i].img_start = imgs;
+        imgs += q.N;
+        const size_t c = (size_t)q.H * q.W * 32;
+        max_chunks = c > max_chunks ? c : max_chunks;
+    }
+    if (imgs > 65535) return fail(ORP_EINVAL, "gn_apply_bf16: too many images");
+    dim3 grid((unsigned)((max_chunks + 2047) / 2048), (unsigned)imgs);
+    gn_apply_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(P);
+    ORP_LAUNCHED();
+    return ORP_OK;
+}
+
 extern "C" int orp_gn_apply_bf16(const void *x, int N, int H, int W, int C, const double *stats, int groups,
                                  const float *gamma, const float *beta, float eps, int relu, const void *up_src, void *y,
                                  void *stream)
 {
-    if (!x || !y || !stats || !gamma || !beta || C != 256 || groups != 32) return fail(ORP_EINVAL, "gn_apply_bf16: needs C=256, 32 groups");
-    int rc = ensure_device();
-    if (rc) return rc;
-    const size_t total = (size_t)N * H * W * 32;
-    gn_apply_bf16_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16 *>(x), N, H, W, stats, gamma, beta, eps, relu,
-        static_cast<const __nv_bfloat16 *>(up_src), static_cast<__nv_bfloat16 *>(y));
-    ORP_LAUNCHED();
-    return ORP_OK;
+    orp_gn_problem q;
+    q.x = x; q.N = N; q.H = H; q.W = W; q.stats = stats; q.up_src = up_src; q.y = y;
+    return orp_gn_apply_bf16_multi(1, &q, C, groups, gamma, beta, eps, relu, stream);
 }

@@ -149,7 +149,7 @@ select_keys_kernel(const uint8_t *__restrict__ keep, const uint8_t *__restrict__
         if (!(keep[r] && valid[r])) mid = 0xFFFFFFFFull;
         else if (counts[b] > cap) mid = (uint64_t)(~orderable(dets[r * 9 + 8]));   // score descending (top bit clear: never 0xFFFFFFFF)
         else mid = 0;                                                                              // candidate order
-        keys[r] = ((uint64_t)b << 52) | (mid << 20) | (uint64_t)i;
+        keys[r] = ((uint64_t)b << 32) | mid;        // the sort is stable: ties keep candidate order
         vals[r] = i;
     }
 }
@@ -239,7 +239,9 @@ extern "C" int orp_head_postprocess(int nlevels, const float *const *cls, const 
     int32_t *sv1 = Sc.get<int32_t>(total), *sv2 = Sc.get<int32_t>(total);
     size_t tb1 = 0, tb2 = 0;
     if (nsort) cub::DeviceRadixSort::SortPairs(nullptr, tb1, k1, k2, v1, v2, (int)nsort, 0, 64, st);
-    cub::DeviceRadixSort::SortPairs(nullptr, tb2, sk1, sk2, sv1, sv2, (int)total, 0, 64, st);
+    int sel_bits = 33;                                                 // (image << 32 | score key)
+    while ((1ll << (sel_bits - 32)) < (long long)B) ++sel_bits;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb2, sk1, sk2, sv1, sv2, (int)total, 0, sel_bits, st);
     uint8_t *tmp = Sc.get<uint8_t>(tb1 > tb2 ? tb1 : tb2);
     if (!tmp || !sv2 || !keep) return fail(ORP_ECUDA, "orp_head_postprocess: scratch allocation failed");
 
@@ -255,15 +257,15 @@ extern "C" int orp_head_postprocess(int nlevels, const float *const *cls, const 
     decode_kernel<<<ceil_div((long long)B * S, 128), 128, 0, st>>>(L, v2, score_thr, scale_factor, O);
     ORP_LAUNCHED();
     rc = run_nms(O.dets, O.segs, (int)total, iou_thr, ORP_NMS_EXACT64, ORP_UNION_NAN_KEEPS, ORP_ORDER_INDEX_ASC, nullptr,
-                 nullptr, st, keep, true);
+                 nullptr, st, keep, true, B * num_cls);
     if (rc) return rc;
     ORP_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * B, st));
     count_kernel<<<dim3(32, B), 256, 0, st>>>(keep, O.valid, (int)per_img, B, counts);
     ORP_LAUNCHED();
     select_keys_kernel<<<grid_for(total, 256), 256, 0, st>>>(keep, O.valid, O.dets, counts, (int)per_img, B, max_per_img, sk1, sv1);
     ORP_LAUNCHED();
-    ORP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb2, sk1, sk2, sv1, sv2, (int)total, 0, 64, st));
-    count_launches(9);
+    ORP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb2, sk1, sk2, sv1, sv2, (int)total, 0, sel_bits, st));
+    count_launches((sel_bits + 7) / 8 + 1);
     gather_kernel<<<dim3(ceil_div(max_per_img, 128), B), 128, 0, st>>>(sv2, counts, O.dets, O.rp, O.box, (int)per_img, S,
                                                                      num_cls, max_per_img, B, dets_out, labels_out, counts_out);
     ORP_LAUNCHED();

@@ -531,8 +531,17 @@ nms_flags_kernel(const uint8_t *__restrict__ status, const int32_t *__restrict__
 // flags_out (optional): uint8 [n], 1 where the box (by ORIGINAL index) survives; when given, keep_out /
 // num_out may be NULL and the compaction is skipped (used by the fused head post-processing).
 int run_nms(const float *dets, const int32_t *segments, int n, double thr, int iou_mode, int union_mode,
-            int order, int64_t *keep_out, int32_t *num_out, cudaStream_t st, uint8_t *flags_out, bool no_sync)
+            int order, int64_t *keep_out, int32_t *num_out, cudaStream_t st, uint8_t *flags_out, bool no_sync, int seg_limit)
 {
+    // sweep keys are (segment << 32 | xmin); with a known segment bound only the low 32 + seg_bits bits need sorting
+    // (seg_bits chosen so that the all-ones field of non-finite boxes still sorts after every real segment)
+    if (!segments) seg_limit = 1;
+    int sweep_bits = 64;
+    if (seg_limit > 0) {
+        int b = 1;
+        while ((1ll << b) <= (long long)seg_limit) ++b;
+        sweep_bits = 32 + b;
+    }
     if (n < 0 || (!flags_out && !num_out) || (n > 0 && (!dets || (!flags_out && !keep_out))))
         return fail(ORP_EINVAL, "orp_rnms: null pointer or negative n");
     if (iou_mode != ORP_NMS_EXACT64 && iou_mode != ORP_NMS_COMPAT32) return fail(ORP_EINVAL, "orp_rnms: bad iou_mode");
@@ -561,7 +570,7 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
 
     size_t tb1 = 0, tb2 = 0, tb3 = 0, tb4 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb1, score_key, score_key2, iota, order_r, n, 0, 32, st);
-    cub::DeviceRadixSort::SortPairs(nullptr, tb2, sweep_key, sweep_key2, iota, perm, n, 0, 64, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb2, sweep_key, sweep_key2, iota, perm, n, 0, sweep_bits, st);
     cub::DeviceScan::ExclusiveSum(nullptr, tb3, indeg, offs, n + 1, st);
     if (keep_out && num_out) cub::DeviceSelect::Flagged(nullptr, tb4, vals, flags, keep_out, num_out, n, st);
     size_t tb = tb1 > tb2 ? tb1 : tb2;
@@ -594,8 +603,8 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
         if (!edges) return fail(ORP_ECUDA, "orp_rnms: edge buffer allocation failed");
         if (iou_mode == ORP_NMS_EXACT64) {
             if (attempt == 0) {
-                ORP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb2, sweep_key, sweep_key2, iota, perm, n, 0, 64, st));
-                count_launches(8);
+                ORP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb2, sweep_key, sweep_key2, iota, perm, n, 0, sweep_bits, st));
+                count_launches((sweep_bits + 7) / 8);
                 nms_gather_kernel<<<G, T, 0, st>>>(dets, segments, perm, sweep_key2, rank, n, aabb, v01, v23,
                                                    rk, sg, area, nvalid);
                 ORP_LAUNCHED();
@@ -689,7 +698,7 @@ extern "C" int orp_rnms(const float *dets, const int32_t *segments, int n, doubl
                         int union_mode, int order, int64_t *keep_out, int32_t *num_out, void *stream)
 {
     return orp::run_nms(dets, segments, n, iou_thr, iou_mode, union_mode, order, keep_out, num_out,
-                        static_cast<cudaStream_t>(stream), nullptr, false);
+                        static_cast<cudaStream_t>(stream), nullptr, false, 0);
 }
 
 extern "C" int orp_rnms_last_sweep_ms(float *ms)
@@ -741,7 +750,7 @@ extern "C" int orp_poly_nms_host(int *keep_out, int *num_out, const float *polys
         // the caller sorted by score already (poly_nms.pyx:19-21); our stable descending sort
         // reproduces that order exactly, so SCORE_DESC output == positions in the sorted input
         rc = run_nms(d, nullptr, polys_num, (double)nms_overlap_thresh, ORP_NMS_EXACT64, ORP_UNION_GUARD,
-                     ORP_ORDER_SCORE_DESC, k, cnt, st, nullptr, false);
+                     ORP_ORDER_SCORE_DESC, k, cnt, st, nullptr, false, 1);
         if (rc) break;
         int32_t hc = 0;
         if (cudaMemcpyAsync(&hc, cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||

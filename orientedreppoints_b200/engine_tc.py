@@ -94,17 +94,33 @@ class EngineTC:
     def conv(self, x, L, relu=False, residual=None, out_f32=False):
         return self.conv_multi([x], L, relu, None if residual is None else [residual], out_f32)[0]
 
-    def gn(self, x, norm, relu=False, up=None, stats=None):
-        n, h, w, c = x.shape
+    def gn_multi(self, xs, norm, relu=False, ups=None, stats=None):
+        """GroupNorm(32, 256) (+ReLU, + nearest-upsampled top-down add) of several tensors sharing gamma / beta
+        in one launch; stats: per-tensor double [N,32,2] sums (from the conv epilogue) or None to compute them"""
         st = _lib.current_stream_ptr()
+        k = len(xs)
         if stats is None:
-            stats = torch.zeros((n, 32, 2), dtype=torch.float64, device=self.device)
-            _lib.check(self.lib.orp_gn_stats_bf16(_lib.ptr(x), n, h * w, c, 32, _lib.ptr(stats), st), "orp_gn_stats_bf16")
-        y = torch.empty_like(x)
-        _lib.check(self.lib.orp_gn_apply_bf16(_lib.ptr(x), n, h, w, c, _lib.ptr(stats), 32, _lib.ptr(norm.gamma),
-                                              _lib.ptr(norm.beta), 1e-5, int(relu), _lib.ptr(up), _lib.ptr(y), st),
-                   "orp_gn_apply_bf16")
-        return y
+            stats = []
+            for x in xs:
+                n, h, w, c = x.shape
+                s = torch.zeros((n, 32, 2), dtype=torch.float64, device=self.device)
+                _lib.check(self.lib.orp_gn_stats_bf16(_lib.ptr(x), n, h * w, c, 32, _lib.ptr(s), st), "orp_gn_stats_bf16")
+                stats.append(s)
+        ys = [torch.empty_like(x) for x in xs]
+        arr = (_lib.GnProblem * k)()
+        for i, x in enumerate(xs):
+            assert x.shape[3] == 256 and x.dtype == torch.bfloat16
+            arr[i].x = x.data_ptr()
+            arr[i].N, arr[i].H, arr[i].W = x.shape[0], x.shape[1], x.shape[2]
+            arr[i].stats = stats[i].data_ptr()
+            arr[i].up_src = ups[i].data_ptr() if ups is not None and ups[i] is not None else None
+            arr[i].y = ys[i].data_ptr()
+        _lib.check(self.lib.orp_gn_apply_bf16_multi(k, arr, 256, 32, _lib.ptr(norm.gamma), _lib.ptr(norm.beta), 1e-5,
+                                                    int(relu), st), "orp_gn_apply_bf16_multi")
+        return ys
+
+    def gn(self, x, norm, relu=False, up=None, stats=None):
+        return self.gn_multi([x], norm, relu=relu, ups=[up], stats=None if stats is None else [stats])[0]
 
     def conv_gn(self, x, L, norm, relu=False, up=None):
         st = torch.zeros((x.shape[0], 32, 2), dtype=torch.float64, device=self.device)
@@ -114,7 +130,7 @@ class EngineTC:
     def conv_gn_multi(self, xs, L, norm, relu=False):
         sts = torch.zeros((len(xs), xs[0].shape[0], 32, 2), dtype=torch.float64, device=self.device)
         ys = self.conv_multi(xs, L, stats=[sts[i] for i in range(len(xs))])
-        return [self.gn(y, norm, relu=relu, stats=sts[i]) for i, y in enumerate(ys)]
+        return self.gn_multi(ys, norm, relu=relu, stats=[sts[i] for i in range(len(xs))])
 
     def maxpool(self, x):
         n, h, w, c = x.shape

@@ -33,7 +33,8 @@ def _worker(rank, world, port, q):
     buf, cnt = gather.pack(dets, labels, counts)
     ab, ac = gather.all_gather_detections(buf, cnt)
     out = gather.interleave(ab, ac, dataset_len=5)       # 6 slots, dataset of 5: last one is sampler padding
-    q.put((rank, [(d.clone(), l.clone()) for d, l in out], dets, labels, counts))
+    # numpy payloads are pickled by value (torch tensors travel as shared-memory handles that die with the worker)
+    q.put((rank, [(d.numpy().copy(), l.numpy().copy()) for d, l in out], dets.numpy(), labels.numpy(), counts.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -56,4 +57,4 @@ def test_all_gather_interleave_world2():
             src_rank, slot = i % world, i // world
             sd, sl, sc = per_rank[src_rank]
             k = int(sc[slot])
-            assert d.shape == (k, 27) and torch.equal(d, sd[slot, :k]) and torch.equal(l, sl[slot, :k])
+            assert d.shape == (k, 27) and (d == sd[slot, :k]).all() and (l == sl[slot, :k]).all()

@@ -257,6 +257,12 @@ int orp_stem_conv_bf16(const float *img_nchw, int N, int H, int W, const void *w
  * conv1 of the ResNet stem as a GEMM: NCHW fp32 image -> bf16 [N,Ho,Wo,192] rows
  * (k = (kh*7+kw)*3 + c, zero above 147) */
 int orp_stem_im2col_bf16(const float *img_nchw, int N, int H, int W, void *out, void *stream);
+/* default stem path: space-to-depth bf16 copy of the image, out[n][Y][X][(dy*2+dx)*3+c] = img[n][c][2(Y-2)+dy][2(X-2)+dx]
+ * (zero outside, channels 12-15 zero; [N, H/2+3, W/2+3, 16]) - 1/12 of the im2col bytes - and conv1 as a 4x4 stride-1
+ * convolution over it: w256 bf16 [64][4][4][16] with ky = 2kh'+dy-1, kx = 2kw'+dx-1.  H, W (of the IMAGE) even. */
+int orp_stem_s2d_bf16(const float *img_nchw, int N, int H, int W, void *out, void *stream);
+int orp_stem_conv_s2d_bf16(const void *x_s2d, int N, int H, int W, const void *w256, const float *bias, int relu,
+                           void *out, void *stream);
 int orp_maxpool3x3s2_bf16(const void *x, int N, int H, int W, int C, void *y, void *stream);
 /* GroupNorm over bf16 NHWC with C = 256, 32 groups: statistics (double [N,32,2], zeroed by caller) + apply */
 int orp_gn_stats_bf16(const void *x, int N, int HW, int C, int groups, double *stats, void *stream);

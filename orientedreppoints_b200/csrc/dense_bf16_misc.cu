@@ -229,6 +229,60 @@ int grid_for(size_t items, int threads)
 
 using namespace orp;
 
+namespace orp {
+namespace {
+// Space-to-depth form of the stem input: out[n][Y][X][(dy*2+dx)*3 + c] = img[n][c][2(Y-2)+dy][2(X-2)+dx] (zero outside
+// the image, channels 12-15 zero), Y in [0, H/2+3), X in [0, W/2+3).  conv1 (7x7, stride 2, pad 3; resnet.py:495)
+// is then a 4x4 stride-1 convolution over 16 channels, which the tensor-core kernel reads straight through TMA.
+__global__ void __launch_bounds__(256)
+stem_s2d_kernel(const float *__restrict__ img, int N, int H, int W, __nv_bfloat16 *__restrict__ out)
+{
+    const int Hp = H / 2 + 3, Wp = W / 2 + 3;
+    const size_t total = (size_t)N * Hp * Wp;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int X = (int)(i % Wp);
+        const size_t t = i / Wp;
+        const int Y = (int)(t % Hp), n = (int)(t / Hp);
+        const int y0 = 2 * (Y - 2), x0 = 2 * (X - 2);
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = 0.f;
+        if (x0 >= 0 && x0 + 1 < W) {
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const int y = y0 + dy;
+                if (y < 0 || y >= H) continue;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float2 p = *reinterpret_cast<const float2 *>(img + (((size_t)n * 3 + c) * H + y) * W + x0);
+                    v[(dy * 2 + 0) * 3 + c] = p.x;
+                    v[(dy * 2 + 1) * 3 + c] = p.y;
+                }
+            }
+        }
+        uint4 o0 = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+        uint4 o1 = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+        uint4 *op = reinterpret_cast<uint4 *>(out + i * 16);
+        op[0] = o0;
+        op[1] = o1;
+    }
+}
+}  // namespace
+}  // namespace orp
+
+extern "C" int orp_stem_s2d_bf16(const float *img_nchw, int N, int H, int W, void *out, void *stream)
+{
+    using namespace orp;
+    if (!img_nchw || !out || N < 1 || H < 2 || W < 2 || (H & 1) || (W & 1)) return fail(ORP_EINVAL, "stem_s2d_bf16: needs even H, W");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const size_t total = (size_t)N * (H / 2 + 3) * (W / 2 + 3);
+    stem_s2d_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(img_nchw, N, H, W,
+                                                                                        static_cast<__nv_bfloat16 *>(out));
+    ORP_LAUNCHED();
+    return ORP_OK;
+}
+
 extern "C" int orp_stem_im2col_bf16(const float *img_nchw, int N, int H, int W, void *out, void *stream)
 {
     if (!img_nchw || !out || N <= 0) return fail(ORP_EINVAL, "stem_im2col_bf16: bad arguments");

@@ -40,8 +40,24 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;                       // bf16 elements per K block = 128 bytes = one swizzle row
 constexpr int kABytes = kBM * kBK * 2;        // 16 KiB
 
+// division by a runtime constant as multiply-high + shift (Granlund-Montgomery); exact for 0 <= n < 2^31
+struct FastDiv {
+    uint32_t mul, shr, d;
+    __host__ void set(uint32_t div)
+    {
+        d = div;
+        uint32_t l = 0;
+        while ((1ull << l) < div) ++l;
+        shr = l;
+        mul = (uint32_t)(((1ull << 32) * ((1ull << l) - div)) / div + 1);
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return (__umulhi(n, mul) + n) >> shr; }   // n < 2^31: no overflow
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t &q, uint32_t &r) const { q = div(n); r = n - q * d; }
+};
+
 struct Problem {
     int N, H, W, Ho, Wo;
+    FastDiv fd_tw, fd_th;                     // / tiles_w, / tiles_h
     int BW, BH, BI;                           // tile box: BW*BH*BI == 128 output pixels (powers of two)
     int lbw, lbh;                             // log2(BW), log2(BH)
     int tiles_w, tiles_h, tiles_i, tile_start;
@@ -66,6 +82,7 @@ struct alignas(64) TcParams {
     int gn_fused;                             // GroupNorm statistics accumulated in the TMA epilogue (Cout == 256)
     int stem;                                 // producers build conv1's 7x7/2 im2col rows from the NCHW fp32 image
     int nprob, num_m_tiles, n_tiles_n, num_tiles;
+    FastDiv fd_ntn;                           // / n_tiles_n
     int KH, KW, Cin, cin_blocks, stride, pad, Cout, relu;
     const float *bias;
 };
@@ -217,17 +234,20 @@ struct Ring {
 
 __device__ __forceinline__ void decode_tile(const TcParams &P, int tile, int &pi, int &wb, int &hb, int &ib, int &nt)
 {
-    nt = tile % P.n_tiles_n;
-    const int mt = tile / P.n_tiles_n;
+    uint32_t mt_u, nt_u;
+    P.fd_ntn.divmod((uint32_t)tile, mt_u, nt_u);
+    nt = (int)nt_u;
+    const int mt = (int)mt_u;
     pi = 0;
 #pragma unroll
     for (int k = 1; k < kMaxProb; ++k)
         if (k < P.nprob && mt >= P.prob[k].tile_start) pi = k;
     const Problem &pr = P.prob[pi];
     const int local = mt - pr.tile_start;
-    wb = local % pr.tiles_w;
-    hb = (local / pr.tiles_w) % pr.tiles_h;
-    ib = local / (pr.tiles_w * pr.tiles_h);
+    uint32_t rest, wb_u, ib_u, hb_u;
+    pr.fd_tw.divmod((uint32_t)local, rest, wb_u);
+    pr.fd_th.divmod(rest, ib_u, hb_u);
+    wb = (int)wb_u; hb = (int)hb_u; ib = (int)ib_u;
 }
 
 // 64 x 64 bf16 identity, the B operand that adds a residual tile into the accumulator
@@ -357,7 +377,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
             int res_groups = 0;
             if (!DEFORM && P.res_mma) {
-                const int nt = tile % P.n_tiles_n;
+                const int nt = tile - (int)P.fd_ntn.div((uint32_t)tile) * P.n_tiles_n;
                 for (int g = 0; g < BN / 64 && nt * BN + g * 64 < P.Cout; ++g) ++res_groups;
             }
             mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -928,6 +948,18 @@ extern "C" int orp_stem_conv_bf16(const float *img_nchw, int N, int H, int W, co
     return conv2d_bf16_impl(1, &q, w192, 64, 64, 1, 1, 192, 1, 0, bias, relu, 0, 1, 1, stream);
 }
 
+extern "C" int orp_stem_conv_s2d_bf16(const void *x_s2d, int N, int H, int W, const void *w256, const float *bias, int relu,
+                                      void *out, void *stream)
+{
+    if (!x_s2d || !w256 || !out || N < 1 || H < 2 || W < 2 || (H & 1) || (W & 1))
+        return fail(ORP_EINVAL, "stem_conv_s2d_bf16: needs even H, W");
+    orp_tc_problem q;
+    memset(&q, 0, sizeof(q));
+    q.x = x_s2d;
+    q.N = N; q.H = H / 2 + 3; q.W = W / 2; q.out = out;     // 4 x 1 taps over rows, 64 virtual channels, no padding
+    return conv2d_bf16_impl(1, &q, w256, 64, 64, 4, 1, 64, 1, 0, bias, relu, 0, 0, 2, stream);
+}
+
 static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *w, int Cout, int Cout_padded, int KH,
                             int KW, int Cin, int stride, int pad, const float *bias, int relu, int out_f32,
                             int deform, int stem, void *stream)
@@ -958,8 +990,9 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     // a partial last channel block is zero-filled by TMA (A operand) and by the weight layout (B operand)
     P.nprob = nprob; P.KH = KH; P.KW = KW; P.Cin = Cin; P.cin_blocks = (Cin + kBK - 1) / kBK;
     P.stride = stride; P.pad = pad;
-    P.Cout = Cout; P.relu = relu; P.bias = bias; P.stem = stem;
+    P.Cout = Cout; P.relu = relu; P.bias = bias; P.stem = (stem == 1) ? 1 : 0;
     P.n_tiles_n = Cout_padded / BN;
+    P.fd_ntn.set((uint32_t)P.n_tiles_n);
     int mt = 0;
     for (int i = 0; i < nprob; ++i) {
         const orp_tc_problem &q = probs[i];
@@ -967,7 +1000,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
         pr.N = q.N; pr.H = q.H; pr.W = q.W;
         pr.Ho = (q.H + 2 * pad - (KH - 1) - 1) / stride + 1;
         pr.Wo = (q.W + 2 * pad - (KW - 1) - 1) / stride + 1;
-        if (stem) { pr.Ho = (q.H + 6 - 7) / 2 + 1; pr.Wo = (q.W + 6 - 7) / 2 + 1; }
+        if (stem == 1) { pr.Ho = (q.H + 6 - 7) / 2 + 1; pr.Wo = (q.W + 6 - 7) / 2 + 1; }
         if (pr.Ho <= 0 || pr.Wo <= 0 || !q.x || !q.out) return fail(ORP_EINVAL, "conv2d_bf16: bad problem");
         pr.BW = pow2_floor(pr.Wo < 128 ? pr.Wo : 128);
         if (stride * pr.BW > 256) pr.BW = 256 / stride;
@@ -977,6 +1010,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
         pr.lbh = 0; while ((1 << pr.lbh) < pr.BH) ++pr.lbh;
         pr.tiles_w = ceil_div(pr.Wo, pr.BW); pr.tiles_h = ceil_div(pr.Ho, pr.BH); pr.tiles_i = ceil_div(pr.N, pr.BI);
         pr.tile_start = mt;
+        pr.fd_tw.set((uint32_t)pr.tiles_w); pr.fd_th.set((uint32_t)pr.tiles_h);
         mt += pr.tiles_w * pr.tiles_h * pr.tiles_i;
         pr.out = q.out; pr.res = static_cast<const __nv_bfloat16 *>(q.residual_bf16); pr.res32 = q.residual_f32;
         pr.x = static_cast<const __nv_bfloat16 *>(q.x); pr.offset = q.offset; pr.gn_stats = q.gn_stats;
@@ -984,6 +1018,13 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
         if (!deform) {
             cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.N};
             cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)q.W * Cin * 2, (cuuint64_t)q.H * q.W * Cin * 2};
+            if (stem == 2) {
+                // space-to-depth stem: the tensor is [N, H, W + 3, 16]; a 64-element "pixel" row of the GEMM is the
+                // 4 horizontally adjacent 16-channel pixels starting at w, so consecutive w overlap (stride 32 bytes)
+                gstr[0] = 32;
+                gstr[1] = (cuuint64_t)(q.W + 3) * 32;
+                gstr[2] = (cuuint64_t)q.H * (q.W + 3) * 32;
+            }
             cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(pr.BW * stride), (cuuint32_t)(pr.BH * stride), (cuuint32_t)pr.BI};
             cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
             CUresult r = enc(&P.tmA[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(q.x), gdim, gstr, box, estr,

@@ -42,21 +42,54 @@ class EngineTC:
         assert img.shape[1] == 3
         return img                                                   # the stem kernel reads the NCHW image directly
 
-    def stem(self, img, L, materialise=True):
-        tc = self._stem_tc(L)
+    def _stem_s2d_tc(self, L):
+        """conv1 weights for the space-to-depth form: [64][kh' 0..3][kw' 0..3][16] with ky = 2kh'+dy-1,
+        kx = 2kw'+dx-1, channel (dy*2+dx)*3+c (zero where ky/kx fall outside 0..6, channels 12-15 zero)"""
+        if getattr(L, "tc_s2d", None) is None:
+            w = L.w_raw                                              # [64, 7, 7, 3]
+            wp = torch.zeros((64, 4, 4, 16), dtype=torch.float32)
+            for khp in range(4):
+                for dy in range(2):
+                    ky = 2 * khp + dy - 1
+                    if not 0 <= ky <= 6:
+                        continue
+                    for kwp in range(4):
+                        for dx in range(2):
+                            kx = 2 * kwp + dx - 1
+                            if not 0 <= kx <= 6:
+                                continue
+                            ch = (dy * 2 + dx) * 3
+                            wp[:, khp, kwp, ch:ch + 3] = w[:, ky, kx, :]
+            L.tc_s2d = wp.reshape(64, 256).to(self.device, torch.bfloat16).contiguous()
+        return L.tc_s2d
+
+    def stem(self, img, L, materialise=True, mode=None):
+        """conv1 + folded BN + ReLU.  mode "s2d" (default): space-to-depth bf16 copy of the image (1/12 of the im2col
+        bytes) + a 4x4 stride-1 tensor-core convolution reading it through TMA; "im2col": K=192 rows materialised in
+        HBM + plain GEMM; "direct": im2col rows built in shared memory by producer warps (no HBM intermediate)."""
         n, _, h, w = img.shape
+        if mode is None:
+            mode = "s2d" if materialise else "direct"
+        if mode == "s2d" and (h % 2 or w % 2):
+            mode = "im2col"
         ho, wo = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
         y = torch.empty((n, ho, wo, 64), dtype=torch.bfloat16, device=self.device)
-        # default: im2col rows in HBM + plain GEMM (557 us per 4 tiles); the direct producer variant
-        # (orp_stem_conv_bf16, no HBM intermediate) is LSU-bound in its current scalar-gather form (1136 us)
-        if materialise:
+        st = _lib.current_stream_ptr()
+        if mode == "s2d":
+            ws = self._stem_s2d_tc(L)
+            xs = torch.empty((n, h // 2 + 3, w // 2 + 3, 16), dtype=torch.bfloat16, device=self.device)
+            _lib.check(self.lib.orp_stem_s2d_bf16(_lib.ptr(img), n, h, w, _lib.ptr(xs), st), "orp_stem_s2d_bf16")
+            _lib.check(self.lib.orp_stem_conv_s2d_bf16(_lib.ptr(xs), n, h, w, _lib.ptr(ws), _lib.ptr(L.bias), 1, _lib.ptr(y),
+                                                       st), "orp_stem_conv_s2d_bf16")
+            return y
+        tc = self._stem_tc(L)
+        if mode == "im2col":
             cols = torch.empty((n, ho, wo, 192), dtype=torch.bfloat16, device=self.device)
-            _lib.check(self.lib.orp_stem_im2col_bf16(_lib.ptr(img), n, h, w, _lib.ptr(cols), _lib.current_stream_ptr()),
-                       "orp_stem_im2col_bf16")
+            _lib.check(self.lib.orp_stem_im2col_bf16(_lib.ptr(img), n, h, w, _lib.ptr(cols), st), "orp_stem_im2col_bf16")
             self._launch([cols], [y], tc, 64, 1, 1, 192, 1, 0, L.bias, True, False, False)
             return y
         _lib.check(self.lib.orp_stem_conv_bf16(_lib.ptr(img), n, h, w, _lib.ptr(tc["w"]), _lib.ptr(L.bias), 1, _lib.ptr(y),
-                                               _lib.current_stream_ptr()), "orp_stem_conv_bf16")
+                                               st), "orp_stem_conv_bf16")
         return y
 
     def _launch(self, xs, ys, tc, cout, kh, kw, cin, stride, pad, bias, relu, out_f32, deform, res=None, res32=None,

@@ -204,10 +204,31 @@ def test_stem_conv_tc_direct_equals_materialised_im2col(cuda, sd):
     det = OrientedRepPointsDetector(sd, 50, cuda, "bf16")
     for (n, h, w) in ((2, 256, 320), (1, 250, 198)):
         img = torch.randn(n, 3, h, w, generator=torch.Generator().manual_seed(h)).to(cuda)
-        a = det.eng.stem(img, det.stem, materialise=False)
-        b = det.eng.stem(img, det.stem, materialise=True)
+        a = det.eng.stem(img, det.stem, mode="direct")
+        b = det.eng.stem(img, det.stem, mode="im2col")
         assert a.shape == b.shape == (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 64)
         assert torch.equal(a, b)
+
+
+def test_stem_space_to_depth_form(cuda, sd):
+    """default stem path (space-to-depth copy + 4x4 stride-1 conv through TMA) against the im2col GEMM (same bf16
+    operands, different accumulation order) and against torch's conv2d on the bf16-rounded operands
+    (resnet.py:495 conv1 + folded norm1 + ReLU)"""
+    import torch.nn.functional as F
+    from orientedreppoints_b200.detector import OrientedRepPointsDetector
+    det = OrientedRepPointsDetector(sd, 50, cuda, "bf16")
+    for (n, h, w) in ((2, 256, 320), (1, 250, 198), (3, 64, 66), (1, 1024, 1024)):
+        img = torch.randn(n, 3, h, w, generator=torch.Generator().manual_seed(h)).to(cuda)
+        a = det.eng.stem(img, det.stem)                       # s2d
+        b = det.eng.stem(img, det.stem, mode="im2col")
+        assert a.shape == b.shape
+        diff = (a.float() - b.float()).abs()
+        assert float(diff.max()) <= 2e-2 * max(1.0, float(b.float().abs().max())), float(diff.max())
+        assert float((diff > 0).float().mean()) < 0.05        # only last-bit flips of the bf16 rounding
+        wq = det.stem.w_raw.to(cuda).bfloat16().double().permute(0, 3, 1, 2)            # [64,3,7,7]
+        ref = F.relu(F.conv2d(img.bfloat16().double(), wq, det.stem.bias.double().to(cuda), stride=2, padding=3))
+        err = (a.double().permute(0, 3, 1, 2) - ref).abs().max()
+        assert float(err) <= 1e-2 * max(1.0, float(ref.abs().max())), float(err)
 
 
 def test_r101_graph_bf16_vs_f32_engine(cuda):

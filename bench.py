@@ -257,10 +257,13 @@ def run_reference_tile(args, rank, world):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = random_state_dict(50, seed=0, reference_init=True)
-    img = torch.randn(1, 3, 1024, 1024, generator=torch.Generator().manual_seed(1000))
+    tile_u8 = torch.randint(0, 256, (1, 1024, 1024, 3), generator=torch.Generator().manual_seed(1000), dtype=torch.uint8)
+    mean = torch.tensor([123.675, 116.28, 103.53]); stdinv = 1.0 / torch.tensor([58.395, 57.12, 57.375])
 
     def step():
         with torch.no_grad():
+            # Normalize (to_rgb, mean, std) + ImageToTensor of the test pipeline, as the reference does them on the host
+            img = ((tile_u8.float().flip(-1) - mean) * stdinv).permute(0, 3, 1, 2).contiguous()
             outs, _ = tr.forward_dense(sd, img)
             return tr.get_bboxes_single([o[0][0] for o in outs], [o[2][0] for o in outs], score_thr=0.0)
 

@@ -263,6 +263,11 @@ int orp_stem_im2col_bf16(const float *img_nchw, int N, int H, int W, void *out, 
 int orp_stem_s2d_bf16(const float *img_nchw, int N, int H, int W, void *out, void *stream);
 int orp_stem_conv_s2d_bf16(const void *x_s2d, int N, int H, int W, const void *w256, const float *bias, int relu,
                            void *out, void *stream);
+/* the same space-to-depth tensor straight from the decoded uint8 HWC image [N,H,W,3] with the pipeline's Normalize
+ * (mmdet/datasets/pipelines/transforms.py:Normalize -> mmcv.imnormalize; mean/std per MODEL channel, host pointers;
+ * to_rgb swaps the image's channel order) fused in: a step uploads 3 bytes per pixel instead of 12 */
+int orp_stem_s2d_u8_bf16(const uint8_t *img_hwc, int N, int H, int W, const float *mean, const float *std, int to_rgb,
+                         void *out, void *stream);
 int orp_maxpool3x3s2_bf16(const void *x, int N, int H, int W, int C, void *y, void *stream);
 /* GroupNorm over bf16 NHWC with C = 256, 32 groups: statistics (double [N,32,2], zeroed by caller) + apply */
 int orp_gn_stats_bf16(const void *x, int N, int HW, int C, int groups, double *stats, void *stream);

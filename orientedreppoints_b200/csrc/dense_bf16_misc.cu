@@ -267,8 +267,73 @@ stem_s2d_kernel(const float *__restrict__ img, int N, int H, int W, __nv_bfloat1
         op[1] = o1;
     }
 }
+
+// The same from the decoded image as the data pipeline holds it: uint8 HWC [N,H,W,3] (cv2 channel order).  The
+// Normalize step of the test pipeline (mmdet/datasets/pipelines/transforms.py Normalize -> mmcv.imnormalize:
+// optional BGR->RGB, (x - mean) * (1/std) in fp32) is applied on the fly, so a step uploads 3 bytes per pixel
+// instead of 12.  mean / stdinv are indexed by MODEL channel c; model channel c is image channel (to_rgb ? 2-c : c).
+__global__ void __launch_bounds__(256)
+stem_s2d_u8_kernel(const uint8_t *__restrict__ img, int N, int H, int W, float3 mean, float3 stdinv, int to_rgb,
+                   __nv_bfloat16 *__restrict__ out)
+{
+    const int Hp = H / 2 + 3, Wp = W / 2 + 3;
+    const size_t total = (size_t)N * Hp * Wp;
+    const float mu[3] = {mean.x, mean.y, mean.z}, si[3] = {stdinv.x, stdinv.y, stdinv.z};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int X = (int)(i % Wp);
+        const size_t t = i / Wp;
+        const int Y = (int)(t % Hp), n = (int)(t / Hp);
+        const int y0 = 2 * (Y - 2), x0 = 2 * (X - 2);
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = 0.f;
+        if (x0 >= 0 && x0 + 1 < W) {
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const int y = y0 + dy;
+                if (y < 0 || y >= H) continue;
+                const uint8_t *p = img + (((size_t)n * H + y) * W + x0) * 3;     // 6 bytes: two pixels
+                // x0 even -> the 6 bytes start at an even address
+                const uint16_t a = *reinterpret_cast<const uint16_t *>(p), b = *reinterpret_cast<const uint16_t *>(p + 2),
+                               c2 = *reinterpret_cast<const uint16_t *>(p + 4);
+                const uint8_t px[6] = {(uint8_t)(a & 0xff), (uint8_t)(a >> 8), (uint8_t)(b & 0xff), (uint8_t)(b >> 8),
+                                       (uint8_t)(c2 & 0xff), (uint8_t)(c2 >> 8)};
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int sc = to_rgb ? 2 - c : c;
+                        v[(dy * 2 + dx) * 3 + c] = ((float)px[dx * 3 + sc] - mu[c]) * si[c];
+                    }
+            }
+        }
+        uint4 o0 = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+        uint4 o1 = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+        uint4 *op = reinterpret_cast<uint4 *>(out + i * 16);
+        op[0] = o0;
+        op[1] = o1;
+    }
+}
 }  // namespace
 }  // namespace orp
+
+extern "C" int orp_stem_s2d_u8_bf16(const uint8_t *img_hwc, int N, int H, int W, const float *mean, const float *std,
+                                    int to_rgb, void *out, void *stream)
+{
+    using namespace orp;
+    if (!img_hwc || !out || !mean || !std || N < 1 || H < 2 || W < 2 || (H & 1) || (W & 1))
+        return fail(ORP_EINVAL, "stem_s2d_u8_bf16: needs even H, W");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const float3 mu = make_float3(mean[0], mean[1], mean[2]);
+    // mmcv.imnormalize: stdinv = 1 / np.float64(std), applied to the float32 image
+    const float3 si = make_float3((float)(1.0 / (double)std[0]), (float)(1.0 / (double)std[1]), (float)(1.0 / (double)std[2]));
+    const size_t total = (size_t)N * (H / 2 + 3) * (W / 2 + 3);
+    stem_s2d_u8_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(img_hwc, N, H, W, mu, si, to_rgb,
+                                                                                           static_cast<__nv_bfloat16 *>(out));
+    ORP_LAUNCHED();
+    return ORP_OK;
+}
 
 extern "C" int orp_stem_s2d_bf16(const float *img_nchw, int N, int H, int W, void *out, void *stream)
 {

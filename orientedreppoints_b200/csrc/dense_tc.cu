@@ -81,6 +81,7 @@ struct alignas(64) TcParams {
     int res_mma;                              // residual added by the tensor core: extra K blocks  R[128x64] * I[64x64]
     int gn_fused;                             // GroupNorm statistics accumulated in the TMA epilogue (Cout == 256)
     int stem;                                 // producers build conv1's 7x7/2 im2col rows from the NCHW fp32 image
+    int s2d_stem;                             // conv1 in space-to-depth form (host bookkeeping: 147 useful K of 256)
     int nprob, num_m_tiles, n_tiles_n, num_tiles;
     FastDiv fd_ntn;                           // / n_tiles_n
     int KH, KW, Cin, cin_blocks, stride, pad, Cout, relu;
@@ -886,7 +887,8 @@ int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st, int stag
         ORP_CUDA(cudaEventRecord(g_tc_ev[slot][0], st));
         double fl = 0;
         for (int i = 0; i < P.nprob; ++i)
-            fl += 2.0 * P.prob[i].N * P.prob[i].Ho * P.prob[i].Wo * (double)P.Cout * P.KH * P.KW * (P.stem ? 147 : P.Cin);
+            fl += 2.0 * P.prob[i].N * P.prob[i].Ho * P.prob[i].Wo * (double)P.Cout *
+                  (P.s2d_stem ? 147.0 : (double)P.KH * P.KW * (P.stem ? 147 : P.Cin));   // algorithmic K, not the padded one
         g_tc_flops += fl;
         g_tc_trace[slot] = TcTrace{P.nprob, P.prob[0].N, P.prob[0].H, P.prob[0].W, P.Cin, P.Cout, P.KH, P.stride, DEFORM ? 1 : 0,
                                    BN, P.num_tiles, grid, fl};
@@ -990,7 +992,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     // a partial last channel block is zero-filled by TMA (A operand) and by the weight layout (B operand)
     P.nprob = nprob; P.KH = KH; P.KW = KW; P.Cin = Cin; P.cin_blocks = (Cin + kBK - 1) / kBK;
     P.stride = stride; P.pad = pad;
-    P.Cout = Cout; P.relu = relu; P.bias = bias; P.stem = (stem == 1) ? 1 : 0;
+    P.Cout = Cout; P.relu = relu; P.bias = bias; P.stem = (stem == 1) ? 1 : 0; P.s2d_stem = (stem == 2) ? 1 : 0;
     P.n_tiles_n = Cout_padded / BN;
     P.fd_ntn.set((uint32_t)P.n_tiles_n);
     int mt = 0;

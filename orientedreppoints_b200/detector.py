@@ -124,6 +124,8 @@ class OrientedRepPointsDetector:
                              max_per_img=2000)                         # configs/dota/orientedrepoints_r50_demo.py:62-67
         if test_cfg:
             self.test_cfg.update(test_cfg)
+        # configs/dota/orientedrepoints_r50_demo.py:72-73; used when simple_test() is given decoded uint8 HWC tiles
+        self.img_norm_cfg = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_rgb=True)
         if precision == "fp32":
             self.eng = EngineF32(self.device)
         elif precision == "bf16":
@@ -194,9 +196,23 @@ class OrientedRepPointsDetector:
         self._load_head(sd)
 
     # ------------------------------------------------------------------ dense graph
+    def normalize(self, img):
+        """decoded uint8 HWC tiles [N,H,W,3] -> the pipeline's Normalize + ImageToTensor on the device
+        (mmdet/datasets/pipelines/transforms.py:Normalize, formating.py:ImageToTensor); float NCHW input passes through"""
+        if img.dtype != torch.uint8:
+            return img
+        c = self.img_norm_cfg
+        x = img.to(self.device).float()
+        if c["to_rgb"]:
+            x = x.flip(-1)
+        mean = torch.tensor(c["mean"], dtype=torch.float32, device=self.device)
+        stdinv = torch.tensor([1.0 / v for v in c["std"]], dtype=torch.float64).float().to(self.device)
+        return ((x - mean) * stdinv).permute(0, 3, 1, 2).contiguous()
+
     def extract_feat(self, img):
         e = self.eng
         if self.depth == "swin_tiny":
+            img = self.normalize(img)
             c3, c4, c5 = self.swin.forward(img)
             l2 = e.conv_gn(c5, *self.lat[2])
             l1 = e.conv_gn(c4, *self.lat[1], up=l2)
@@ -205,8 +221,11 @@ class OrientedRepPointsDetector:
             outs.append(self.swin.subsample2(outs[-1]))
             outs.append(self.swin.subsample2(outs[-1]))
             return outs
-        x = e.prepare_input(img)
-        x = e.maxpool(e.stem(x, self.stem))
+        if img.dtype == torch.uint8 and hasattr(e, "stem_u8") and img.shape[1] % 2 == 0 and img.shape[2] % 2 == 0:
+            x = e.maxpool(e.stem_u8(img, self.stem, self.img_norm_cfg))     # Normalize fused into the stem input transform
+        else:
+            x = e.prepare_input(self.normalize(img))
+            x = e.maxpool(e.stem(x, self.stem))
         feats = []
         for stage in self.blocks:
             for blk in stage:
@@ -245,12 +264,12 @@ class OrientedRepPointsDetector:
         return self.head(feats), feats
 
     # ------------------------------------------------------------------ CUDA graph of the dense graph
-    def capture(self, img_shape):
+    def capture(self, img_shape, dtype=torch.float32):
         """Capture backbone + FPN + head for a fixed input shape into ONE CUDA graph (static buffers): the
         ~180 kernel launches of a step become a single graph launch, which removes the host-side launch
         cost that otherwise dominates a one-tile step.  simple_test() replays it when the shape matches."""
         shape = tuple(img_shape)
-        self._g_img = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        self._g_img = torch.zeros(shape, dtype=dtype, device=self.device)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -261,7 +280,7 @@ class OrientedRepPointsDetector:
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._g_out = self.forward_dense(self._g_img)
-        self._g_shape = shape
+        self._g_shape = (shape, dtype)
         return self
 
     def forward_dense_graph(self, img):
@@ -272,7 +291,7 @@ class OrientedRepPointsDetector:
     # ------------------------------------------------------------------ simple_test
     def simple_test(self, img, img_metas=None, rescale=True, return_tensors=False):
         from .core.get_bboxes import get_bboxes
-        if getattr(self, "_g_shape", None) == tuple(img.shape):
+        if getattr(self, "_g_shape", None) == (tuple(img.shape), img.dtype):
             outs, _ = self.forward_dense_graph(img)
         else:
             outs, _ = self.forward_dense(img)

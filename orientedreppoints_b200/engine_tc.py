@@ -92,6 +92,24 @@ class EngineTC:
                                                st), "orp_stem_conv_bf16")
         return y
 
+    def stem_u8(self, img_u8, L, norm_cfg):
+        """conv1 + folded BN + ReLU from decoded uint8 HWC tiles [N,H,W,3]; Normalize (mean/std/to_rgb of the test
+        pipeline) is applied inside the space-to-depth transform kernel"""
+        import ctypes
+        n, h, w, c = img_u8.shape
+        assert c == 3 and img_u8.dtype == torch.uint8 and img_u8.is_contiguous() and h % 2 == 0 and w % 2 == 0
+        st = _lib.current_stream_ptr()
+        ws = self._stem_s2d_tc(L)
+        xs = torch.empty((n, h // 2 + 3, w // 2 + 3, 16), dtype=torch.bfloat16, device=self.device)
+        mean = (ctypes.c_float * 3)(*norm_cfg["mean"])
+        std = (ctypes.c_float * 3)(*norm_cfg["std"])
+        _lib.check(self.lib.orp_stem_s2d_u8_bf16(_lib.ptr(img_u8), n, h, w, mean, std, int(bool(norm_cfg["to_rgb"])),
+                                                 _lib.ptr(xs), st), "orp_stem_s2d_u8_bf16")
+        y = torch.empty((n, h // 2, w // 2, 64), dtype=torch.bfloat16, device=self.device)
+        _lib.check(self.lib.orp_stem_conv_s2d_bf16(_lib.ptr(xs), n, h, w, _lib.ptr(ws), _lib.ptr(L.bias), 1, _lib.ptr(y), st),
+                   "orp_stem_conv_s2d_bf16")
+        return y
+
     def _launch(self, xs, ys, tc, cout, kh, kw, cin, stride, pad, bias, relu, out_f32, deform, res=None, res32=None,
                 offsets=None, stats=None):
         n = len(xs)

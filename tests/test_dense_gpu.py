@@ -231,6 +231,32 @@ def test_stem_space_to_depth_form(cuda, sd):
         assert float(err) <= 1e-2 * max(1.0, float(ref.abs().max())), float(err)
 
 
+def test_uint8_tiles_normalize_fused_into_stem(cuda, sd):
+    """decoded uint8 HWC tiles: Normalize (mmdet/datasets/pipelines/transforms.py:Normalize -> mmcv.imnormalize,
+    mean/std/to_rgb of configs/dota/orientedrepoints_r50_demo.py:72-73) fused into the stem input transform gives
+    exactly what normalising first and feeding the float NCHW tensor gives"""
+    from orientedreppoints_b200.detector import OrientedRepPointsDetector
+    det = OrientedRepPointsDetector(sd, 50, cuda, "bf16", test_cfg=dict(score_thr=0.0))
+    u8 = torch.randint(0, 256, (2, 128, 160, 3), generator=torch.Generator().manual_seed(5), dtype=torch.uint8).to(cuda)
+    x = det.normalize(u8)
+    assert x.shape == (2, 3, 128, 160) and x.dtype == torch.float32
+    ref = ((u8.cpu().double().flip(-1) - torch.tensor([123.675, 116.28, 103.53], dtype=torch.float64))
+           / torch.tensor([58.395, 57.12, 57.375], dtype=torch.float64)).permute(0, 3, 1, 2)
+    assert float((x.cpu().double() - ref).abs().max()) < 1e-5
+    a = det.eng.stem_u8(u8, det.stem, det.img_norm_cfg)
+    b = det.eng.stem(x, det.stem)
+    assert torch.equal(a, b)
+    ra = det.simple_test(u8, return_tensors=True)
+    rb = det.simple_test(x, return_tensors=True)
+    for (da, la), (db, lb) in zip(ra, rb):
+        assert torch.equal(da, db) and torch.equal(la, lb)
+    # fp32 engine takes the same tiles (normalised by torch ops on the device)
+    d32 = OrientedRepPointsDetector(sd, 50, cuda, "fp32")
+    o_u8, _ = d32.forward_dense(u8)
+    o_f, _ = d32.forward_dense(x)
+    assert torch.allclose(o_u8[0][0], o_f[0][0], rtol=1e-4, atol=1e-4)      # fp32 GroupNorm statistics use atomics: not bit-reproducible
+
+
 def test_r101_graph_bf16_vs_f32_engine(cuda):
     """BASELINE.json configs[3] backbone: same code path with STAGE_BLOCKS[101] = (3, 4, 23, 3)"""
     from orientedreppoints_b200.detector import OrientedRepPointsDetector

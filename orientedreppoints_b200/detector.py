@@ -205,9 +205,12 @@ class OrientedRepPointsDetector:
         x = img.to(self.device).float()
         if c["to_rgb"]:
             x = x.flip(-1)
-        mean = torch.tensor(c["mean"], dtype=torch.float32, device=self.device)
-        stdinv = torch.tensor([1.0 / v for v in c["std"]], dtype=torch.float64).float().to(self.device)
-        return ((x - mean) * stdinv).permute(0, 3, 1, 2).contiguous()
+        key = (tuple(c["mean"]), tuple(c["std"]))
+        if getattr(self, "_norm_key", None) != key:                   # device constants, made once (not inside a graph capture)
+            self._norm_mean = torch.tensor(c["mean"], dtype=torch.float32).to(self.device)
+            self._norm_stdinv = torch.tensor([1.0 / v for v in c["std"]], dtype=torch.float64).float().to(self.device)
+            self._norm_key = key
+        return ((x - self._norm_mean) * self._norm_stdinv).permute(0, 3, 1, 2).contiguous()
 
     def extract_feat(self, img):
         e = self.eng

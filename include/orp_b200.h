@@ -288,6 +288,15 @@ int orp_gn_apply_bf16_multi(int nprob, const orp_gn_problem *probs, int C, int g
                             const float *beta, float eps, int relu, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Tile producer (DOTA_devkit/SplitOnlyImage_multi_process.py:38-49 saveimagepatches): cut ntiles windows of
+ * subsize x subsize pixels at origins[t] = (left, up) out of one decoded uint8 HWC image resident on the device,
+ * zero padded where a window leaves the image; out: uint8 [ntiles, subsize, subsize, C] - the batch
+ * OrientedRepPointsDetector.simple_test() consumes.  origins: device int32 [ntiles, 2]; subsize*C % 4 == 0.
+ */
+int orp_split_tiles_u8(const uint8_t *img_hwc, int H, int W, int C, const int32_t *origins, int ntiles, int subsize,
+                       uint8_t *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Swin-T backbone pieces (mmdet/models/backbones/swin_transformer.py); the Linear layers are
  * orp_conv2d_bf16 1x1 convolutions (relu = 2 selects the exact GELU epilogue)
  * ---------------------------------------------------------------------------------------- */

@@ -315,3 +315,51 @@ class OrientedRepPointsDetector:
             return results
         from .core.transforms import rbbox2result
         return [rbbox2result(d, l, 16) for d, l in results]
+
+    # ------------------------------------------------------------------ aug_test (multi-scale / flip merge)
+    @staticmethod
+    def rbbox_flip(rbboxes, img_shape, direction='horizontal'):
+        """orientedreppoints_detector.py:48-73: x -> w - x - 1 (or y -> h - y - 1) on every vertex"""
+        assert rbboxes.shape[-1] % 8 == 0
+        flipped = rbboxes.clone()
+        if direction == 'horizontal':
+            flipped[..., 0::2] = img_shape[1] - rbboxes[..., 0::2] - 1
+        elif direction == 'vertical':
+            flipped[..., 1::2] = img_shape[0] - rbboxes[..., 1::2] - 1
+        else:
+            raise ValueError('Invalid flipping direction "{}"'.format(direction))
+        return flipped
+
+    def merge_aug_results(self, aug_bboxes, aug_scores, img_metas):
+        """orientedreppoints_detector.py:81-110: map every view's boxes back (un-flip, / scale_factor), concatenate"""
+        recovered = []
+        for bboxes, info in zip(aug_bboxes, img_metas):
+            m = info[0]
+            b = self.rbbox_flip(bboxes, m['img_shape']) if m['flip'] else bboxes
+            recovered.append(b / m['scale_factor'])
+        bboxes = torch.cat(recovered, dim=0)
+        if aug_scores is None:
+            return bboxes
+        return bboxes, torch.cat(aug_scores, dim=0)
+
+    def aug_test(self, imgs, img_metas, rescale=False):
+        """orientedreppoints_detector.py:112-144.  imgs: list of views, each ONE image (float NCHW [1,3,H,W] or uint8
+        HWC [1,H,W,3]); img_metas: list of [dict(img_shape, scale_factor, flip)].  Raw candidates of all views
+        (get_bboxes(nms=False), head :778-779) are concatenated and go through ONE multiclass_rnms."""
+        from .core.bbox_nms import multiclass_rnms
+        from .core.get_bboxes import get_bboxes
+        from .core.transforms import rbbox2result
+        aug_bboxes, aug_scores = [], []
+        for img, meta in zip(imgs, img_metas):
+            assert img.shape[0] == 1, "aug_test: one image per view"
+            outs, _ = self.forward_dense(img)
+            b, sc = get_bboxes([o[0] for o in outs], [o[2] for o in outs], STRIDES, meta, self.test_cfg, False, nms=False)[0]
+            aug_bboxes.append(b)
+            aug_scores.append(sc)
+        merged_bboxes, merged_scores = self.merge_aug_results(aug_bboxes, aug_scores, img_metas)
+        det_bboxes, det_labels = multiclass_rnms(merged_bboxes, merged_scores, self.test_cfg['score_thr'],
+                                                 self.test_cfg['nms'], self.test_cfg['max_per_img'])
+        if not rescale:
+            det_bboxes = det_bboxes.clone()
+            det_bboxes[:, :8] *= img_metas[0][0]['scale_factor']
+        return rbbox2result(det_bboxes, det_labels, 16)

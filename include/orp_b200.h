@@ -143,6 +143,12 @@ int orp_quad_iou_matrix(const float *quads_a, int n, const float *quads_b, int k
  * (DOTA_devkit/polyiou.cpp:108-128) - the batched device equivalent of the SWIG call. */
 int orp_iou_poly_f64_pairs(const double *p8, const double *q8, int n, double *out, void *stream);
 
+/* IoU between the convex hull of each 9-point set and each quadrilateral: pts18 [N,18] (x0,y0,...,x8,y8),
+ * quads8 [K,8] -> out [N,K] fp32, device resident.  Replaces convex_iou_cuda
+ * (mmdet/ops/iou/src/convex_iou_kernel.cu:268-360; python side mmdet/ops/iou/iou_wrapper.py:21-30 convex_iou /
+ * convex_overlaps).  fp64 gift-wrapping hull + fp64 polygon clipping as in the reference, float result. */
+int orp_convex_iou(const float *pts18, int n, const float *quads8, int k, float *out, void *stream);
+
 /* detectron2-style rotated boxes (cx,cy,w,h,theta in RADIANS as modified at
  * mmdet/ops/box_iou_rotated/src/box_iou_rotated_utils.h:59-62) -> N x M IoU; replaces
  * box_iou_rotated_cuda (box_iou_rotated_cuda.cu:13-62). */

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "liborp_oracle.so")
-SOURCES = ["oracle_geom.c", "oracle_minarearect.c", "oracle_dcn.c"]
+SOURCES = ["oracle_geom.c", "oracle_minarearect.c", "oracle_dcn.c", "oracle_convex_iou.c"]
 
 
 def build(force=False, verbose=False):

@@ -202,3 +202,21 @@ def minarearect(pts18):
     hn = np.zeros(n, np.int32)
     lib().orc_minarearect(_f(p), n, _f(out), _i(hmap), _i(hn))
     return out, hmap, hn
+
+
+def convex_iou(pts18, quads8):
+    """IoU(hull of 9 points, quadrilateral) for every (point set, quad) pair: [N,18] x [K,8] -> float32 [N,K]
+    (restated mmdet/ops/iou/src/convex_iou_kernel.cu:268-312)"""
+    p = np.ascontiguousarray(pts18, dtype=np.float32).reshape(-1, 18)
+    q = np.ascontiguousarray(quads8, dtype=np.float32).reshape(-1, 8)
+    out = np.empty((p.shape[0], q.shape[0]), dtype=np.float32)
+    lib().orc_convex_iou(p.ctypes.data_as(ctypes.c_void_p), p.shape[0], q.ctypes.data_as(ctypes.c_void_p), q.shape[0],
+                         out.ctypes.data_as(ctypes.c_void_p))
+    return out
+
+
+def convex_hull9(pts18):
+    p = np.ascontiguousarray(pts18, dtype=np.float32).reshape(18)
+    ring = np.zeros(18, dtype=np.float64)
+    n = lib().orc_convex_hull9(p.ctypes.data_as(ctypes.c_void_p), ring.ctypes.data_as(ctypes.c_void_p))
+    return ring[:2 * n].reshape(-1, 2)

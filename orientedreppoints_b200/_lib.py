@@ -70,6 +70,7 @@ SIGNATURES = {
     "orp_stem_conv_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "orp_stem_im2col_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "orp_stem_s2d_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "orp_convex_iou": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "orp_split_tiles_u8": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "orp_stem_s2d_u8_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "orp_stem_conv_s2d_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),

@@ -107,7 +107,8 @@ __device__ __forceinline__ int half_plane_cut(Pt<T> *v, int n, Pt<T> a, Pt<T> b,
     return k;
 }
 
-template <typename T>
+// ABS = false: convex_iou_kernel.cu:124-127 keeps the sign of the clipped triangle's area (polyiou.cpp:86 takes fabs)
+template <typename T, bool ABS = true>
 __device__ __forceinline__ T fan_pair(Pt<T> a, Pt<T> b, Pt<T> c, Pt<T> d)
 {
     using R = Rn<T>;
@@ -127,7 +128,7 @@ __device__ __forceinline__ T fan_pair(Pt<T> a, Pt<T> b, Pt<T> c, Pt<T> d)
     n = half_plane_cut(ring, n, c, d, tmp);
     n = half_plane_cut(ring, n, d, o, tmp);
     T ar = ring_area(ring, n);
-    ar = ar < 0 ? -ar : ar;
+    if (ABS) ar = ar < 0 ? -ar : ar;
     return (s1 * s2 == -1) ? -ar : ar;
 }
 

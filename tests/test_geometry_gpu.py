@@ -244,3 +244,27 @@ def test_box_iou_rotated_vs_compiled_reference(cuda, golden):
     assert out.shape == g["iou"].shape and out.dtype == np.float32
     assert np.abs(out - g["iou"]).max() < 1e-4            # north_star tolerance; both are fp32 centre-shifted evaluations
     assert (g["iou"] > 0.05).sum() > 100
+
+
+def test_convex_iou_matches_oracle_bit_exact(cuda, po):
+    """orp_convex_iou (fp64 hull + fp64 clipping, float result) == the CPU oracle's sequence, bit for bit,
+    through the reference-shaped python mirror (mmdet/ops/iou/iou_wrapper.py:21-30)"""
+    from orientedreppoints_b200.ops import convex_iou, convex_overlaps
+    rng = np.random.RandomState(3)
+    n, k = 700, 40
+    pts = (rng.rand(n, 9, 2) * 60 + rng.rand(n, 1, 2) * 100).astype(np.float32)
+    # degenerate sets: duplicated points, collinear triples, axis-aligned grids (exact ties in the gift wrapping)
+    pts[:50, 3:] = pts[:50, :1]
+    pts[50:100, 2] = (pts[50:100, 0] + pts[50:100, 1]) / 2
+    gx, gy = np.meshgrid(np.arange(3, dtype=np.float32), np.arange(3, dtype=np.float32))
+    pts[100:150] = (np.stack([gx.ravel(), gy.ravel()], 1)[None] * 8 + rng.randint(0, 100, size=(50, 1, 2))).astype(np.float32)
+    quads = po.gen_rotated_boxes(k, seed=4, extent=160.0, wmin=10, wmax=80)[:, :8].astype(np.float32)
+    ref = po.convex_iou(pts.reshape(n, 18), quads)
+    got = convex_iou(torch.from_numpy(pts.reshape(n, 18)).to(cuda), torch.from_numpy(quads).to(cuda))
+    assert got.shape == (n, k) and got.is_cuda
+    g = got.cpu().numpy()
+    assert np.array_equal(g.view(np.uint32), ref.view(np.uint32)), float(np.abs(g - ref).max())
+    assert torch.equal(convex_overlaps(torch.from_numpy(quads).to(cuda), torch.from_numpy(pts.reshape(n, 18)).to(cuda)), got.t())
+    with pytest.raises(TypeError):
+        convex_iou(torch.zeros(1, 18), torch.zeros(1, 8))
+    assert convex_iou(torch.zeros(0, 18, device=cuda), torch.from_numpy(quads).to(cuda)).shape == (0, k)

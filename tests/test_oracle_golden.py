@@ -111,3 +111,42 @@ def test_minarearect_oracle_analytic(po):
     # all points identical -> a degenerate rectangle at that point
     box, _, hn = po.minarearect(np.full((1, 18), 3.0, np.float32))
     assert np.allclose(box, 3.0, atol=1e-5)
+
+
+def _convex_cases(po, n, k, seed):
+    rng = np.random.RandomState(seed)
+    pts = (rng.rand(n, 9, 2) * 60 + rng.rand(n, 1, 2) * 100).astype(np.float32)
+    quads = po.gen_rotated_boxes(k, seed=seed + 1, extent=160.0, wmin=10, wmax=80)[:, :8].astype(np.float32)
+    return pts.reshape(n, 18), quads
+
+
+def test_convex_iou_oracle_agrees_with_opencv(po):
+    """the convex_iou restatement (mmdet/ops/iou/src/convex_iou_kernel.cu:139-312; CUDA-only in the reference, so
+    unpinned by it) against an independent implementation: cv2.convexHull + cv2.intersectConvexConvex"""
+    cv2 = pytest.importorskip("cv2")
+    pts, quads = _convex_cases(po, 120, 25, 0)
+    out = po.convex_iou(pts, quads)
+    assert out.shape == (120, 25) and out.dtype == np.float32
+    worst = 0.0
+    for i in range(pts.shape[0]):
+        hull = cv2.convexHull(pts[i].reshape(9, 2)).reshape(-1, 2)
+        ha = cv2.contourArea(hull)
+        ring = po.convex_hull9(pts[i])
+        assert ring.shape[0] == hull.shape[0]                       # same hull vertices (general position)
+        for j in range(quads.shape[0]):
+            q = quads[j].reshape(4, 2)
+            ia, _ = cv2.intersectConvexConvex(hull.astype(np.float32), q)
+            iou = ia / (ha + cv2.contourArea(q) - ia)
+            worst = max(worst, abs(iou - float(out[i, j])))
+    assert worst < 1e-5, worst
+    assert (out > 0.05).mean() > 0.05                               # the cases do overlap
+
+
+def test_convex_iou_oracle_analytic(po):
+    # 9 points on/in the unit square -> hull is the square; IoU with the shifted unit square = 1/7 (polyiou.cpp:130-136)
+    sq = np.array([0, 0, 1, 0, 1, 1, 0, 1, .5, .5, .5, 0, 1, .5, .5, 1, 0, .5], dtype=np.float32)
+    q = np.array([[.5, .5, 1.5, .5, 1.5, 1.5, .5, 1.5], [0, 0, 1, 0, 1, 1, 0, 1], [5, 5, 6, 5, 6, 6, 5, 6]], dtype=np.float32)
+    out = po.convex_iou(sq[None], q)[0]
+    assert abs(out[0] - 1.0 / 7.0) < 1e-7 and abs(out[1] - 1.0) < 1e-7 and out[2] == 0.0
+    # orientation of the quadrilateral does not matter (intersectAreaO reverses clockwise rings, :128-129)
+    assert po.convex_iou(sq[None], q[:1, [0, 1, 6, 7, 4, 5, 2, 3]])[0, 0] == out[0]

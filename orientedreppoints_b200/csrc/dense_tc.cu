@@ -325,6 +325,11 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int kblocks = P.KH * P.KW * P.cin_blocks;
+    // Programmatic dependent launch: the next kernel in the stream may start its CTAs (barrier init, TMEM allocation,
+    // descriptor prefetch - the code above) on SMs this grid has already left; nothing above touches global memory,
+    // and everything below (loads AND stores) comes after the wait for the preceding grid to complete and flush.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         // ===================================================== TMA producer
@@ -893,7 +898,21 @@ int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st, int stag
         g_tc_trace[slot] = TcTrace{P.nprob, P.prob[0].N, P.prob[0].H, P.prob[0].W, P.Cin, P.Cout, P.KH, P.stride, DEFORM ? 1 : 0,
                                    BN, P.num_tiles, grid, fl};
     }
-    kern<<<grid, DEFORM ? 448 : 320, smem, st>>>(P, stages);
+    {
+        static const bool pdl = getenv("ORP_TC_NO_PDL") == nullptr;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(DEFORM ? 448u : 320u);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = pdl ? 1 : 0;
+        ORP_CUDA(cudaLaunchKernelEx(&cfg, kern, P, stages));
+    }
     ORP_LAUNCHED();
     if (slot >= 0) ORP_CUDA(cudaEventRecord(g_tc_ev[slot][1], st));
     return ORP_OK;

@@ -79,6 +79,7 @@ struct alignas(64) TcParams {
     int tma_epi, epi_bufs;                    // TMA epilogue on/off; output staging buffers (1 or 2)
     int b_resident;                           // short-K layers: the whole weight slab of this CTA's N tile stays in shared memory
     int res_mma;                              // residual added by the tensor core: extra K blocks  R[128x64] * I[64x64]
+    int epi_split;                            // epilogue-bound layers: the two epilogue warpgroups work on alternate tiles (one per accumulator buffer)
     int gn_fused;                             // GroupNorm statistics accumulated in the TMA epilogue (Cout == 256)
     int stem;                                 // producers build conv1's 7x7/2 im2col rows from the NCHW fp32 image
     int s2d_stem;                             // conv1 in space-to-depth form (host bookkeeping: 147 useful K of 256)
@@ -288,7 +289,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     constexpr int kPitch = HC * 2 + 16;                // bytes per staged row (+16: conflict-free 16-byte accesses)
     uint8_t *stage_out = smem + (size_t)stages * kStageBytes;
     __shared__ uint64_t bars[2 * kStagesMax + 4];
-    __shared__ float s_bias[256];
+    __shared__ __align__(16) float s_bias_all[2][256];
     __shared__ uint64_t bres_bar;                // resident weight slab landed
     __shared__ uint32_t tmem_slot_s;
     uint64_t *full = bars;                       // [stages]  TMA bytes landed (+ producer arrivals when DEFORM)
@@ -312,7 +313,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 mbar_init(&full[s], DEFORM ? 1 + 256 : 1);
                 mbar_init(&empty[s], 1);
             }
-            for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
+            for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], (kWG == 2 && P.epi_split) ? 4 : kEpiWarps); }
             mbar_init(&bres_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -426,13 +427,25 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     } else if (warp < 2 + kEpiWarps) {
         // ===================================================== epilogue (TMEM lane quarter = warp % 4)
         const int q = warp & 3;
-        const int wg = (warp - 2) >> 2;                    // which 32-column slice of a 64-column pass this warp owns
-        const int et = threadIdx.x - 64;                   // 0..kEpiThreads-1 within the epilogue warps
+        const int wg = (warp - 2) >> 2;                    // epilogue warpgroup (0 or 1)
+        // Two ways to use eight epilogue warps.  Default: both warpgroups work on the same tile, each warp owning one
+        // 32-column half of a 64-column pass.  Split (epilogue-bound layers): the warpgroups are independent, group g
+        // drains accumulator buffer g (= every second tile of this CTA) with its own staging tiles, barriers and bias
+        // copy, so the fixed latencies of one group's pass (barriers, TMEM load, store issue) overlap the other's.
+        const bool split = (kWG == 2) && P.epi_split;
+        const int grp = split ? wg : 0;
+        const int et = split ? ((threadIdx.x - 64) & 127) : (threadIdx.x - 64);   // thread index inside the group
+        const int nthr = split ? 128 : kEpiThreads;
+        const int bar_a = 1 + 3 * grp, bar_b = 3 + 2 * grp;                     // named barriers (1,3) / (4,5); 2 = producers
+        const int ch0 = split ? 0 : wg, chs = split ? 1 : kWG;
+        float *s_bias = s_bias_all[grp];
+        auto bar_sync = [](int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); };
         int ob = 0;                                        // staging ring position (TMA epilogue)
         int bias_nt = -1;                                  // N tile whose bias slice is staged in s_bias
-        int acc = 0;
+        int acc = split ? wg : 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x + (split ? wg * (int)gridDim.x : 0); tile < P.num_tiles;
+             tile += (split ? 2 : 1) * (int)gridDim.x) {
             int pi, wb, hb, ib, nt;
             decode_tile(P, tile, pi, wb, hb, ib, nt);
             const Problem &pr = P.prob[pi];
@@ -473,13 +486,13 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 // tile and leave with cp.async.bulk.tensor (coalescing and partial-tile clipping by hardware).  A
                 // residual is already in the accumulator (added by the tensor core, see the MMA warp).
                 // With eight epilogue warps each warp owns one 32-column half of the pass.
-                const uint32_t obuf_u = smem_u32(stage_out);                                   // [epi_bufs][16 KiB]
+                const uint32_t obuf_u = smem_u32(stage_out) + (uint32_t)(grp * P.epi_bufs) * 16384u;   // [epi_bufs][16 KiB] per group
                 const uint32_t bias_u = smem_u32(s_bias);
                 const bool io = (et == 0);
                 constexpr int kPasses = BN / 64;
                 if (nt != bias_nt) {                                     // bias slice changes only with the N tile
-                    named_bar<1, kEpiThreads>();                         // previous tile's bias reads are done
-                    for (int c = et; c < BN; c += kEpiThreads) s_bias[c] = (P.bias && nt * BN + c < P.Cout) ? P.bias[nt * BN + c] : 0.f;
+                    bar_sync(bar_a, nthr);                               // previous tile's bias reads are done
+                    for (int c = et; c < BN; c += nthr) s_bias[c] = (P.bias && nt * BN + c < P.Cout) ? P.bias[nt * BN + c] : 0.f;
                     bias_nt = nt;
                 }
 #pragma unroll 1
@@ -488,7 +501,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                         if (P.epi_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     }
-                    named_bar<1, kEpiThreads>();                         // staging buffer `ob` is free, bias staged
+                    bar_sync(bar_a, nthr);                               // staging buffer `ob` is free, bias staged
                     if (half == 0) {
                         mbar_wait(&tfull[acc], acc_phase);
                         tcgen05_fence_after();
@@ -496,7 +509,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                     float gn_s = 0.f, gn_q = 0.f;
                     const uint32_t orow = obuf_u + (uint32_t)ob * 16384u + (uint32_t)rrow * 128u;
 #pragma unroll 1
-                    for (int ch = wg; ch < 2; ch += kWG) {
+                    for (int ch = ch0; ch < 2; ch += chs) {
                         uint32_t v[32];
                         tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * 64 + ch * 32), v);
                         // bias slice of these 32 columns: eight back-to-back shared loads, in flight with the TMEM load
@@ -545,7 +558,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             }
                         }
                     }
-                    if (P.gn_fused && lane < 8 && (kWG == 1 || (lane >> 2) == wg)) {
+                    if (P.gn_fused && lane < 8 && (chs == 1 || (lane >> 2) == wg)) {
                         // the 32 rows of a warp belong to one image (host guarantees BW*BH >= 32)
                         const int n_img = ib * pr.BI + ((q * 32) >> (pr.lbw + pr.lbh));
                         if (n_img < pr.N) {
@@ -555,7 +568,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                         }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    named_bar<3, kEpiThreads>();                         // staging written by all
+                    bar_sync(bar_b, nthr);                               // staging written by all
                     if (io) {
                         asm volatile(
                             "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -663,7 +676,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (split) acc_phase ^= 1;                       // this group always drains the same accumulator buffer
+            else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (P.tma_epi && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores drained before exit
     } else if (DEFORM) {
@@ -1082,6 +1096,13 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     const bool mem_bound = any_res || (KH * KW * (Cin / kBK) <= 8);
     P.epi_bufs = mem_bound ? 2 : 1;          // a second staging tile costs compute-bound layers a main-loop stage
     if (const char *e = getenv("ORP_TC_EPI_BUFS")) P.epi_bufs = atoi(e) == 1 ? 1 : 2;
+    // epilogue-bound layers (at most 6 K blocks per tile incl. the residual's; measured: 7-15 lose a little to the
+    // smaller staging/stage budget): independent epilogue warpgroups
+    {
+        const int kb_total = KH * KW * P.cin_blocks + (any_res ? BN / 64 : 0);
+        P.epi_split = (P.tma_epi && !deform && !stem && kb_total <= 6 && !getenv("ORP_TC_NO_SPLIT")) ? 1 : 0;
+        if (P.epi_split) P.epi_bufs = 2;
+    }
     // residual through the tensor core (TMA epilogue only; the staged epilogue adds it itself)
     P.res_mma = (P.tma_epi && any_res) ? 1 : 0;
     if (P.res_mma) {
@@ -1132,7 +1153,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     const int bres_bytes = (P.b_resident ? KH * KW * P.cin_blocks * BN * kBK * 2 : 0) + (P.res_mma ? 8192 : 0);
     const int hc = BN < 64 ? BN : 64;
     int staging = out_f32 ? 0 : 128 * (hc * 2 + 16);
-    if (P.tma_epi) staging = P.epi_bufs * 16384;
+    if (P.tma_epi) staging = P.epi_bufs * 16384 * (P.epi_split ? 2 : 1);
     int stages = (int)((227 * 1024 - 4096 - 1024 - staging - bres_bytes) / stage_bytes);
     if (stages > kStagesMax) stages = kStagesMax;
     if (deform && stages > 3) stages = 3;     // leave L1 capacity for the bilinear gather (corner reuse between neighbouring pixels)

@@ -204,6 +204,26 @@ def run(args, rank, world, local, benchmod):
     e2e_ms = benchmod.max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps, world)
     d2h = sum(int(host_out[0][k].nbytes) for k in ("d", "l", "c"))
 
+    # BASELINE.json configs[1] names a SINGLE tile: the same path with one tile per step (latency-bound: the dense graph
+    # is ~75 launches whatever the batch), reported next to the throughput configuration above
+    single = None
+    if use_graph and batch > 1:
+        img1 = img[:1].contiguous()
+        det.capture(img1.shape, img1.dtype)
+        for _ in range(3):
+            det.simple_test(img1, return_tensors="padded")
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n1 = 20
+        e0.record()
+        for _ in range(n1):
+            det.simple_test(img1, return_tensors="padded")
+        e1.record()
+        torch.cuda.synchronize()
+        ms1 = benchmod.max_over_ranks(e0.elapsed_time(e1) / n1, world)
+        single = {"tiles_per_gpu_per_step": 1, "ms_per_step": ms1, "value": world * 1.0 / (ms1 * 1e-3), "unit": "tiles/s",
+                  "note": "device-timed, inputs resident, no L2 flush between steps"}
+
     pk = benchmod.peaks()
     fl_tile = swin_flops_per_tile() if depth == "swin_tiny" else conv_flops_per_tile(depth)
     line = {
@@ -218,6 +238,7 @@ def run(args, rank, world, local, benchmod):
                    "cuda_graph": "dense graph (backbone+FPN+head) replayed as one CUDA graph" if use_graph else "eager launches",
                    "gather": "one all_gather_into_tensor of [tiles,2000,28] fp32 + counts per step" if world > 1 else "single rank"},
         "gpu_launches": int(launches),
+        "single_tile_step": single,
         "e2e": {"value": world * batch / (e2e_ms * 1e-3), "unit": "tiles/s", "h2d_bytes_per_step": int(img_host.nbytes),
                 "d2h_bytes_per_step": int(d2h), "api": "OrientedRepPointsDetector.simple_test(uint8 HWC tiles) -> rbbox2result lists", "input": "uint8 HWC tiles, Normalize fused into the stem input transform"},
     }

@@ -1,0 +1,63 @@
+"""Host-side logic that needs no GPU: aug_test's box mapping (mmdet/models/detectors/orientedreppoints_detector.py:48-110),
+rbbox2result (mmdet/core/bbox/transforms.py:356-375), detection packing for the all-gather."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_rbbox_flip_matches_reference_formula():
+    from orientedreppoints_b200.detector import OrientedRepPointsDetector as D
+    g = torch.Generator().manual_seed(0)
+    b = torch.rand(7, 16, generator=g) * 100                       # two boxes per row (8*k columns, :51)
+    shape = (120, 200, 3)
+    f = D.rbbox_flip(b, shape)
+    ref = b.clone()
+    for k in (0, 2, 4, 6):                                         # the reference's four strided assignments (:58-61)
+        ref[..., k::8] = shape[1] - b[..., k::8] - 1
+    assert torch.equal(f, ref)
+    v = D.rbbox_flip(b, shape, 'vertical')
+    ref = b.clone()
+    for k in (1, 3, 5, 7):
+        ref[..., k::8] = shape[0] - b[..., k::8] - 1
+    assert torch.equal(v, ref)
+    with pytest.raises(ValueError):
+        D.rbbox_flip(b, shape, 'diagonal')
+    with pytest.raises(AssertionError):
+        D.rbbox_flip(torch.zeros(3, 9), shape)
+
+
+def test_merge_aug_results():
+    from orientedreppoints_b200.detector import OrientedRepPointsDetector as D
+
+    class _Self:
+        rbbox_flip = staticmethod(D.rbbox_flip)
+    b1, b2 = torch.rand(5, 8) * 50, torch.rand(3, 8) * 50
+    s1, s2 = torch.rand(5, 16), torch.rand(3, 16)
+    metas = [[dict(img_shape=(64, 96, 3), scale_factor=0.5, flip=False)], [dict(img_shape=(64, 96, 3), scale_factor=2.0, flip=True)]]
+    mb, ms = D.merge_aug_results(_Self(), [b1, b2], [s1, s2], metas)
+    assert mb.shape == (8, 8) and ms.shape == (8, 16)
+    assert torch.equal(mb[:5], b1 / 0.5) and torch.equal(ms, torch.cat([s1, s2]))
+    assert torch.equal(mb[5:], D.rbbox_flip(b2, (64, 96, 3)) / 2.0)
+    assert torch.equal(D.merge_aug_results(_Self(), [b1, b2], None, metas), mb)
+
+
+def test_rbbox2result_layout():
+    from orientedreppoints_b200.core.transforms import rbbox2result
+    d = torch.arange(6 * 27, dtype=torch.float32).reshape(6, 27)
+    l = torch.tensor([0, 3, 3, 14, 0, 7])
+    r = rbbox2result(d, l, 16)
+    assert len(r) == 15 and [a.shape[0] for a in r] == [2, 0, 0, 2, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1]
+    assert np.array_equal(r[3], d[[1, 2]].numpy())
+    e = rbbox2result(torch.zeros(0, 27), torch.zeros(0, dtype=torch.int64), 16)
+    assert len(e) == 15 and all(a.shape == (0, 9) for a in e)     # the reference's empty case (transforms.py:367-370)
+
+
+def test_pack_roundtrip_single_rank():
+    from orientedreppoints_b200 import gather as G
+    cap, tiles = 8, 2
+    dets = torch.rand(tiles, cap, 27)
+    labels = torch.randint(0, 15, (tiles, cap))
+    counts = torch.tensor([3, 8], dtype=torch.int32)
+    buf, cnt = G.pack(dets, labels, counts)
+    assert buf.shape == (tiles, cap, 28) and torch.equal(cnt, counts)
+    assert torch.equal(buf[0, :3, :27], dets[0, :3]) and torch.equal(buf[1, :, 27].long(), labels[1])

@@ -112,3 +112,39 @@ def test_aug_test_flip_merge(cuda):
     assert torch.allclose(det.rbbox_flip(det.rbbox_flip(d[:, :8], (h, w, 3)), (h, w, 3)), d[:, :8], atol=1e-4)   # w-(w-x-1)-1 in fp32
     with pytest.raises(ValueError):
         det.rbbox_flip(d[:, :8], (h, w, 3), "diagonal")
+
+
+def test_detect_image_equals_file_based_merge(cuda, tmp_path):
+    """tile producer -> detector -> ResultMerge in memory == the same through Task1 files and mergebypoly
+    (the file-based mirror of ResultMerge_multi_process.py, itself checked against the restated reference)"""
+    from orientedreppoints_b200.detector import OrientedRepPointsDetector
+    from orientedreppoints_b200.dota import result_merge as rm
+    from orientedreppoints_b200.dota.pipeline import DOTA_CLASSES, detect_image
+    from orientedreppoints_b200.dota.split_tiles import split_image
+    from orientedreppoints_b200.weights import random_state_dict
+    det = OrientedRepPointsDetector(random_state_dict(50, seed=0, reference_init=True), 50, cuda, "bf16",
+                                    test_cfg=dict(score_thr=0.0, max_per_img=60))
+    img = np.random.RandomState(11).randint(0, 256, size=(420, 610, 3)).astype(np.uint8)
+    # freeze the per-tile results (GroupNorm sums use atomics): both routes consume the same detections
+    tiles, names, origins = split_image(img, "P0042", 1, 256, 64, device=cuda)
+    assert len(names) == 6
+    res = det.simple_test(tiles)
+    det.simple_test = lambda t: res[:t.shape[0]] if t.shape[0] == len(res) else None
+    merged = detect_image(det, img, "P0042", 1, subsize=256, gap=64, batch=16)
+    assert set(merged) == set(DOTA_CLASSES)
+    raw, out = tmp_path / "raw", tmp_path / "merged"
+    rm.write_task1_raw(res, names, DOTA_CLASSES, str(raw))
+    rm.mergebypoly(str(raw), str(out))
+    total = 0
+    for c in DOTA_CLASSES:
+        lines = [l.rstrip("\n") for l in open(out / ("Task1_%s.txt" % c))]
+        assert lines == merged[c], c
+        total += len(lines)
+        for l in lines:
+            sp = l.split(" ")
+            assert sp[0] == "P0042" and len(sp) == 10
+    assert 0 < total <= 6 * 60
+    # coordinates are in image space: a detection of the last tile is shifted by that tile's origin
+    last = names[-1]
+    (l, u) = origins[-1]
+    assert (l, u) == (610 - 256, 420 - 256) and last.endswith("__%d___%d" % (l, u))

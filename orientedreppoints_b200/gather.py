@@ -2,8 +2,8 @@
 (mmdet/apis/test.py:117-147: pickle -> uint8 tensor -> all_gather(shape) -> all_gather(padded bytes) ->
 unpickle) by ONE all_gather_into_tensor of a fixed-layout buffer.
 
-Layout per tile: float32 [max_per_img, 28] = reppoints(18) | box(8) | score | label, zero padded, plus an
-int32 count.  Rank r holds tiles r, r+world, r+2*world, ... (DistributedSampler(shuffle=False) takes
+Layout per tile: float32 [max_per_img + 1, 28]: rows = reppoints(18) | box(8) | score | label, zero padded; the last
+row carries the tile's detection count.  Rank r holds tiles r, r+world, r+2*world, ... (DistributedSampler(shuffle=False) takes
 indices[rank::world], mmdet/datasets/loader/sampler.py:26-32); `interleave` restores dataset order exactly as
 `zip(*part_list)` + truncation does at apis/test.py:143-147.
 """
@@ -12,28 +12,48 @@ import torch.distributed as dist
 
 
 def pack(dets, labels, counts):
-    """padded (dets [T,cap,27], labels [T,cap], counts [T]) -> (buf [T,cap,28], counts)"""
-    buf = torch.cat([dets, labels.to(dets.dtype).unsqueeze(-1)], dim=2)
-    return buf.contiguous(), counts.to(torch.int32).contiguous()
+    """padded (dets [T,cap,27], labels [T,cap], counts [T]) -> (buf [T,cap+1,28], counts): rows 0..cap-1 are the detections,
+    row `cap` carries the tile's count in column 0 (exact in fp32 up to 2^24), so payload and counts travel in ONE collective"""
+    t, cap = dets.shape[0], dets.shape[1]
+    buf = torch.zeros((t, cap + 1, 28), dtype=dets.dtype, device=dets.device)
+    buf[:, :cap, :27] = dets
+    buf[:, :cap, 27] = labels.to(dets.dtype)
+    buf[:, cap, 0] = counts.to(dets.dtype)
+    return buf, counts.to(torch.int32).contiguous()
 
 
-def all_gather_detections(buf, counts, group=None):
-    """-> (all_buf [world,T,cap,28], all_counts [world,T]); a single collective for the payload."""
+class _Gathered:
+    """result of all_gather_detections(async_op=True): wait() -> (all_buf [world,T,cap,28], all_counts [world,T])"""
+
+    def __init__(self, all_buf, work):
+        self._all_buf, self._work = all_buf, work
+
+    def wait(self):
+        if self._work is not None:
+            self._work.wait()            # NCCL: the current stream waits for the collective; gloo: the host does
+            self._work = None
+        cap = self._all_buf.shape[2] - 1
+        return self._all_buf[:, :, :cap], self._all_buf[:, :, cap, 0].to(torch.int32)
+
+
+def all_gather_detections(buf, counts=None, group=None, async_op=False):
+    """buf from pack() -> (all_buf [world,T,cap,28], all_counts [world,T]) with ONE all_gather_into_tensor.
+    async_op=True returns a handle whose wait() gives the same pair: the collective then overlaps whatever the caller
+    launches next (ranks are not forced into lockstep every step)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
-        return buf.unsqueeze(0), counts.unsqueeze(0)
-    all_buf = torch.empty((world,) + tuple(buf.shape), dtype=buf.dtype, device=buf.device)
-    all_cnt = torch.empty((world,) + tuple(counts.shape), dtype=counts.dtype, device=counts.device)
+        h = _Gathered(buf.unsqueeze(0), None)
+        return h if async_op else h.wait()
     if buf.is_cuda:
-        dist.all_gather_into_tensor(all_buf, buf, group=group)
-        dist.all_gather_into_tensor(all_cnt, counts, group=group)
+        all_buf = torch.empty((world,) + tuple(buf.shape), dtype=buf.dtype, device=buf.device)
+        work = dist.all_gather_into_tensor(all_buf, buf.contiguous(), group=group, async_op=True)
+        h = _Gathered(all_buf, work)
     else:   # gloo (CPU tests)
         lb = [torch.empty_like(buf) for _ in range(world)]
-        lc = [torch.empty_like(counts) for _ in range(world)]
-        dist.all_gather(lb, buf, group=group)
-        dist.all_gather(lc, counts, group=group)
-        all_buf, all_cnt = torch.stack(lb), torch.stack(lc)
-    return all_buf, all_cnt
+        work = dist.all_gather(lb, buf, group=group, async_op=True)
+        work.wait()
+        h = _Gathered(torch.stack(lb), None)
+    return h if async_op else h.wait()
 
 
 def interleave(all_buf, all_counts, dataset_len):

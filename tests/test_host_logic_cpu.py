@@ -59,5 +59,13 @@ def test_pack_roundtrip_single_rank():
     labels = torch.randint(0, 15, (tiles, cap))
     counts = torch.tensor([3, 8], dtype=torch.int32)
     buf, cnt = G.pack(dets, labels, counts)
-    assert buf.shape == (tiles, cap, 28) and torch.equal(cnt, counts)
-    assert torch.equal(buf[0, :3, :27], dets[0, :3]) and torch.equal(buf[1, :, 27].long(), labels[1])
+    assert buf.shape == (tiles, cap + 1, 28) and torch.equal(cnt, counts)
+    assert torch.equal(buf[0, :3, :27], dets[0, :3]) and torch.equal(buf[1, :cap, 27].long(), labels[1])
+    assert buf[:, cap, 0].tolist() == [3.0, 8.0]
+    ab, ac = G.all_gather_detections(buf)                         # no process group: world of one
+    assert ab.shape == (1, tiles, cap, 28) and torch.equal(ac, counts.unsqueeze(0))
+    h = G.all_gather_detections(buf, async_op=True)
+    ab2, ac2 = h.wait()
+    assert torch.equal(ab2, ab) and torch.equal(ac2, ac)
+    out = G.interleave(ab, ac, dataset_len=2)
+    assert torch.equal(out[0][0], dets[0, :3]) and torch.equal(out[1][1], labels[1])

@@ -150,3 +150,29 @@ def test_convex_iou_oracle_analytic(po):
     assert abs(out[0] - 1.0 / 7.0) < 1e-7 and abs(out[1] - 1.0) < 1e-7 and out[2] == 0.0
     # orientation of the quadrilateral does not matter (intersectAreaO reverses clockwise rings, :128-129)
     assert po.convex_iou(sq[None], q[:1, [0, 1, 6, 7, 4, 5, 2, 3]])[0, 0] == out[0]
+
+
+def test_result_merge_restatement_equals_reference_output(po):
+    """tile-level Task1 lines -> coordinates back to the image -> per-image poly NMS (thr 0.1) -> merged lines.
+    tests/golden/result_merge.json was produced by the reference's OWN ResultMerge_multi_process.mergesingle
+    (py_cpu_nms_poly_fast and py_cpu_nms_poly, over the SWIG polyiou compiled from its polyiou.cpp); the restatement
+    (result_merge.parse_result_lines + the fp64 CPU oracle NMS + the reference's line format) reproduces every line."""
+    import json
+    from orientedreppoints_b200.dota import result_merge as rm
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "result_merge.json")))
+    assert g["nms_thresh"] == rm.nms_thresh == 0.1
+    names, ids, dets = rm.parse_result_lines(g["lines"])
+    assert names == ["P0003", "P0007", "P0011"] or sorted(names) == ["P0003", "P0007", "P0011"]
+    exp = []
+    for k, name in enumerate(names):                              # dict order = first appearance (mergesingle :190-213)
+        idx = np.nonzero(ids == k)[0]
+        for fast in (True, False):
+            keep = po.nms_poly_f64(dets[idx], g["nms_thresh"], fast=fast)
+            if fast:
+                keep_fast = keep
+            else:
+                assert np.array_equal(keep, keep_fast)
+        for i in idx[keep_fast]:
+            exp.append(name + ' ' + str(float(dets[i, 8])) + ' ' + ' '.join(map(str, [float(v) for v in dets[i, :8]])))
+    assert exp == g["merged"]
+    assert 1000 < len(exp) < len(g["lines"])

@@ -69,3 +69,27 @@ def test_pack_roundtrip_single_rank():
     assert torch.equal(ab2, ab) and torch.equal(ac2, ac)
     out = G.interleave(ab, ac, dataset_len=2)
     assert torch.equal(out[0][0], dets[0, :3]) and torch.equal(out[1][1], labels[1])
+
+
+def test_host_helpers_against_reference_golden():
+    """tests/golden/host_helpers.npz holds outputs of the reference's OWN rbbox2result / rbbox_flip / merge_aug_results
+    (extracted with ast and executed by tests/golden/gen_golden_host.py)"""
+    import os
+    from orientedreppoints_b200.core.transforms import rbbox2result
+    from orientedreppoints_b200.detector import OrientedRepPointsDetector as D
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "host_helpers.npz"))
+    res = rbbox2result(torch.from_numpy(g["r2r_boxes"]), torch.from_numpy(g["r2r_labels"]), 16)
+    assert [a.shape[0] for a in res] == g["r2r_counts"].tolist()
+    assert np.array_equal(np.concatenate(res, 0), g["r2r_concat"])
+    assert tuple(rbbox2result(torch.zeros(0, 27), torch.zeros(0, dtype=torch.long), 16)[0].shape) == tuple(g["r2r_empty_shape"])
+    b = torch.from_numpy(g["flip_in"])
+    assert np.array_equal(D.rbbox_flip(b, (120, 200, 3)).numpy(), g["flip_h"])
+    assert np.array_equal(D.rbbox_flip(b, (120, 200, 3), "vertical").numpy(), g["flip_v"])
+
+    class _Self:
+        rbbox_flip = staticmethod(D.rbbox_flip)
+    metas = [[dict(img_shape=(64, 96, 3), scale_factor=0.5, flip=False)], [dict(img_shape=(64, 96, 3), scale_factor=2.0, flip=True)],
+             [dict(img_shape=(128, 192, 3), scale_factor=1.5, flip=True)]]
+    mb, ms = D.merge_aug_results(_Self(), [torch.from_numpy(g[k]) for k in ("m_b1", "m_b2", "m_b3")],
+                                 [torch.from_numpy(g[k]) for k in ("m_s1", "m_s2", "m_s3")], metas)
+    assert np.array_equal(mb.numpy(), g["m_out_b"]) and np.array_equal(ms.numpy(), g["m_out_s"])

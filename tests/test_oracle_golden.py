@@ -176,3 +176,21 @@ def test_result_merge_restatement_equals_reference_output(po):
             exp.append(name + ' ' + str(float(dets[i, 8])) + ' ' + ' '.join(map(str, [float(v) for v in dets[i, :8]])))
     assert exp == g["merged"]
     assert 1000 < len(exp) < len(g["lines"])
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_postprocess_restatement_equals_reference_python(case):
+    """SURVEY 8 a7 + a9: tests/golden/postprocess.npz holds what the reference's OWN get_bboxes_single
+    (orientedreppoints_head.py:707-779) and multiclass_rnms (bbox_nms.py:93-182) return - extracted with ast and executed by
+    tests/golden/gen_golden_postprocess.py with minaerarect / rnms replaced by their CPU oracles.  The restatement the GPU
+    path is checked against (oracle/torch_reference.py::get_bboxes_single: class segments instead of the coordinate-offset
+    trick, stable sorts) reproduces detections, labels and their order exactly."""
+    import torch
+    from oracle import torch_reference as tr
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "postprocess.npz"))
+    seed, thr, pre, cap = g["c%d_cfg" % case]
+    cls = [torch.from_numpy(g["c%d_cls%d" % (case, l)]) for l in range(5)]
+    pts = [torch.from_numpy(g["c%d_pts%d" % (case, l)]) for l in range(5)]
+    d, l = tr.get_bboxes_single(cls, pts, nms_pre=int(pre), score_thr=float(thr), iou_thr=0.4, max_per_img=int(cap))
+    assert d.shape[0] > 0 and d.shape[1] == 27
+    assert np.array_equal(d.numpy(), g["c%d_dets" % case]) and np.array_equal(l.numpy(), g["c%d_labels" % case])

@@ -194,3 +194,28 @@ def test_postprocess_restatement_equals_reference_python(case):
     d, l = tr.get_bboxes_single(cls, pts, nms_pre=int(pre), score_thr=float(thr), iou_thr=0.4, max_per_img=int(cap))
     assert d.shape[0] > 0 and d.shape[1] == 27
     assert np.array_equal(d.numpy(), g["c%d_dets" % case]) and np.array_equal(l.numpy(), g["c%d_labels" % case])
+
+
+@pytest.mark.parametrize("depth", [50, 101])
+def test_dense_graph_restatement_equals_reference_modules(depth):
+    """tests/golden/dense_ref.npz holds the outputs of the reference's OWN ResNet, FPN and
+    OrientedRepPointsHead modules (imported from /root/reference by tests/golden/gen_golden_dense.py with mmcv/registry
+    plumbing stubbed and DeformConv replaced by the oracle's deform_conv_ref), loaded with strict=True from
+    weights.random_state_dict (same key names) and run in float64.  The functional restatement the GPU engines are checked
+    against (oracle/torch_reference.py::forward_dense) agrees to rounding noise on every FPN level and head output."""
+    import torch
+    from oracle import torch_reference as tr
+    from orientedreppoints_b200.weights import STAGE_BLOCKS, random_state_dict
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dense_ref.npz"))
+    tag = "r%d" % depth
+    d, seed, h, w = [int(v) for v in g[tag + "_meta"]]
+    sd = {k: v.double() for k, v in random_state_dict(d, seed=seed, reference_init=False).items()}
+    img = torch.from_numpy(g[tag + "_img"])
+    with torch.no_grad():
+        outs, feats = tr.forward_dense(sd, img, blocks=STAGE_BLOCKS[d])
+    for l in range(5):
+        ref = torch.from_numpy(g["%s_feat%d" % (tag, l)])
+        assert feats[l].shape == ref.shape and float((feats[l] - ref).abs().max()) < 1e-10 * max(1.0, float(ref.abs().max()))
+        for k, n in enumerate(("cls", "init", "refine")):
+            ref = torch.from_numpy(g["%s_%s%d" % (tag, n, l)])
+            assert float((outs[l][k] - ref).abs().max()) < 1e-10 * max(1.0, float(ref.abs().max())), (l, n)

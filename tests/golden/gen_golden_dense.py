@@ -52,8 +52,8 @@ def install_stubs():
     mmdet = _pkg("mmdet", os.path.join(REF, "mmdet"))
 
     class Registry:
-        def register_module(self, cls):
-            return cls
+        def register_module(self, cls=None):                                         # used both as @R.register_module and @R.register_module()
+            return cls if cls is not None else (lambda c: c)
     utils = types.ModuleType("mmdet.utils")
     utils.get_root_logger = lambda *a, **k: None
     utils.Registry = Registry

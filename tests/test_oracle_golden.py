@@ -219,3 +219,28 @@ def test_dense_graph_restatement_equals_reference_modules(depth):
         for k, n in enumerate(("cls", "init", "refine")):
             ref = torch.from_numpy(g["%s_%s%d" % (tag, n, l)])
             assert float((outs[l][k] - ref).abs().max()) < 1e-10 * max(1.0, float(ref.abs().max())), (l, n)
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_swin_restatement_equals_reference_module(case):
+    """tests/golden/swin_ref.npz holds the outputs of the reference's OWN SwinTransformer
+    (backbones/swin_transformer.py, arguments of configs/dota/orientedrepoints_swin_tiny_demo.py:9-25) and FPN
+    (in_channels [192,384,768], num_outs 5, GN), imported from /root/reference by tests/golden/gen_golden_swin.py (timm /
+    mmcv plumbing stubbed) and run in float64; case 1 exercises the window padding.  The functional restatement the GPU
+    Swin path is checked against (oracle/torch_swin.py) agrees to rounding noise."""
+    import torch
+    from oracle import torch_swin as ts
+    from orientedreppoints_b200.swin import random_swin_state_dict
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "swin_ref.npz"))
+    sd = {k: (v.double() if v.is_floating_point() else v) for k, v in random_swin_state_dict(0).items()}
+    img = torch.from_numpy(g["c%d_img" % case])
+    with torch.no_grad():
+        c = ts.swin_forward(sd, img)
+        f = ts.swin_fpn(sd, c)
+    assert len(c) == 3 and len(f) == 5
+    for i, a in enumerate(c):
+        ref = torch.from_numpy(g["c%d_stage%d" % (case, i)])
+        assert a.shape == ref.shape and float((a - ref).abs().max()) < 1e-10 * max(1.0, float(ref.abs().max()))
+    for i, a in enumerate(f):
+        ref = torch.from_numpy(g["c%d_fpn%d" % (case, i)])
+        assert a.shape == ref.shape and float((a - ref).abs().max()) < 1e-10 * max(1.0, float(ref.abs().max()))

@@ -244,3 +244,27 @@ def test_swin_restatement_equals_reference_module(case):
     for i, a in enumerate(f):
         ref = torch.from_numpy(g["c%d_fpn%d" % (case, i)])
         assert a.shape == ref.shape and float((a - ref).abs().max()) < 1e-10 * max(1.0, float(ref.abs().max()))
+
+
+def test_dcn_oracle_agrees_with_torchvision():
+    """the reference's DeformConv is a CUDA-only extension (mmdet/ops/dcn/src/deform_conv_cuda_kernel.cu), so
+    the im2col restatement the GPU kernels are checked against cannot be pinned by the reference itself.  It is pinned
+    against an independent implementation of the same operator (torchvision.ops.deform_conv2d, CPU): same offset layout
+    (dy, dx per tap), same zero-outside bilinear rule, DCNv1 and DCNv2 (mask), strides / paddings / dilations."""
+    tv = pytest.importorskip("torchvision.ops")
+    import torch
+    from oracle import torch_reference as tr
+    g = torch.Generator().manual_seed(0)
+    for (n, c, h, w, co, s, p, d) in [(2, 8, 11, 13, 6, 1, 1, 1), (1, 16, 9, 9, 4, 2, 1, 1), (1, 4, 10, 12, 5, 1, 2, 2),
+                                      (1, 8, 7, 8, 8, 1, 0, 1)]:
+        x = torch.randn(n, c, h, w, generator=g, dtype=torch.float64)
+        wt = torch.randn(co, c, 3, 3, generator=g, dtype=torch.float64)
+        ho, wo = (h + 2 * p - 2 * d - 1) // s + 1, (w + 2 * p - 2 * d - 1) // s + 1
+        off = torch.randn(n, 18, ho, wo, generator=g, dtype=torch.float64) * 2.5     # many samples leave the image
+        m = torch.rand(n, 9, ho, wo, generator=g, dtype=torch.float64)
+        a = tr.deform_conv_ref(x, off, wt, s, p, d)
+        b = tv.deform_conv2d(x, off, wt, None, stride=s, padding=p, dilation=d)
+        assert a.shape == b.shape and float((a - b).abs().max()) < 1e-10
+        a = tr.deform_conv_ref(x, off, wt, s, p, d, mask=m)
+        b = tv.deform_conv2d(x, off, wt, None, stride=s, padding=p, dilation=d, mask=m)
+        assert float((a - b).abs().max()) < 1e-10

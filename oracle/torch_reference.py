@@ -8,7 +8,13 @@ SURVEY.md 8c), so the layer graph is re-declared here from standard torch layers
   mmdet/ops/dcn/src/deform_conv_cuda_kernel.cu:84-115, 190-243 (deformable im2col) + the GEMM of
   deform_conv_cuda.cpp:231-236
   mmdet/core/post_processing/bbox_nms.py:93-182       (multiclass_rnms, with the class-offset trick)
-PARITY UNPINNED BY THE REFERENCE for these layers (it has no tests); torch 2.11 fp32 is the oracle.
+PINNED (the reference has no tests of its own for these layers, so its code is run instead):
+  * backbone / FPN / head graph: equal to 1e-15 (float64) to the reference's OWN ResNet / FPN / ConvModule /
+    OrientedRepPointsHead modules imported from /root/reference with the mmcv plumbing stubbed
+    (tests/golden/gen_golden_dense.py -> dense_ref.npz, tests/test_oracle_golden.py);
+  * get_bboxes_single + multiclass_rnms: bit-identical detections / labels / order to the reference's OWN python functions
+    run with the two CUDA ops replaced by their oracles (gen_golden_postprocess.py -> postprocess.npz);
+  * deform_conv_ref: the reference's DeformConv is CUDA-only (THC) - pinned against torchvision.ops.deform_conv2d.
 """
 import numpy as np
 import torch

@@ -1,8 +1,9 @@
 """PyTorch re-declaration of the reference's Swin-T backbone + its FPN variant (TEST INFRASTRUCTURE ONLY),
 following mmdet/models/backbones/swin_transformer.py:21-631 (Mlp, window_partition/reverse, WindowAttention,
 SwinTransformerBlock, PatchMerging, BasicLayer mask, PatchEmbed, SwinTransformer.forward with out_indices (1,2,3))
-and mmdet/models/necks/fpn.py:138-178 with start_level=0, add_extra_convs=False.  Parity unpinned by the reference
-(timm / mmcv absent -> the module cannot be imported); torch layers are the oracle."""
+and mmdet/models/necks/fpn.py:138-178 with start_level=0, add_extra_convs=False.  PINNED: equal (float64, incl. the
+window-padding case) to the reference's OWN SwinTransformer + FPN modules imported from /root/reference with timm / mmcv
+plumbing stubbed (tests/golden/gen_golden_swin.py -> swin_ref.npz, tests/test_oracle_golden.py)."""
 import numpy as np
 import torch
 import torch.nn.functional as F

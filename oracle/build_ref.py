@@ -9,8 +9,11 @@ repo; oracle/_ref/ is git-ignored but travels to the GPU box with the gpurun sna
   ref_rnms_cpu.so     mmdet/ops/nms/src/rnms_cpu.cpp unmodified (+ oracle/ref_harness_rnms.cpp)
   ref_box_iou_rotated.so  mmdet/ops/box_iou_rotated/src/box_iou_rotated_cpu.cpp unmodified
 
+  ref_minarearect_dev.so / ref_convex_iou_dev.so   the __device__ functions of minarearect_kernel.cu / convex_iou_kernel.cu
+                      compiled as HOST C++ (the text above their __global__ kernel, piped to g++; see _device_as_host)
+
 Only runs where /root/reference exists (the authoring container).  The reference's CUDA
-sources (mmdet/ops/**/src/*.cu) are NOT buildable: they include THC/THC.h which torch 2.11
+sources (mmdet/ops/**/src/*.cu) are NOT buildable as CUDA: they include THC/THC.h which torch 2.11
 no longer ships - stated in DESIGN.md.
 """
 import os
@@ -34,6 +37,33 @@ def _stale(target, deps):
     return (not os.path.exists(target)) or any(os.path.getmtime(target) < os.path.getmtime(d) for d in deps)
 
 
+_DEVICE_PREFIX = """
+#define __device__
+#define __host__
+#define __global__
+#include <math.h>
+#include <stdio.h>
+#include <algorithm>
+#include <vector>
+"""
+
+
+def _device_as_host(cu_path, cut_marker, wrapper_path, out_so, verbose):
+    """compile the part of a reference .cu file that precedes `cut_marker` (its __device__ functions) as host C++"""
+    if not (os.path.exists(cu_path) and os.path.exists(wrapper_path)):
+        return
+    if not _stale(out_so, [cu_path, wrapper_path, os.path.abspath(__file__)]):
+        return
+    text = open(cu_path).read()
+    cut = text.index(cut_marker)
+    body = "\n".join(l for l in text[:cut].splitlines() if not l.lstrip().startswith("#include"))   # ATen / THC headers
+    unit = _DEVICE_PREFIX + body + "\n" + open(wrapper_path).read()
+    cmd = ["g++", "-x", "c++", "-", "-O2", "-shared", "-fPIC", "-w", "-ffp-contract=off", "-o", out_so]
+    if verbose:
+        print(" ".join(cmd), "  <", cu_path, "(device part) +", wrapper_path)
+    subprocess.run(cmd, input=unit.encode(), check=True)
+
+
 def build(verbose=False, with_torch=True):
     if not os.path.isdir(REF):
         return None
@@ -53,6 +83,14 @@ def build(verbose=False, with_torch=True):
         _run(["g++", "-O2", "-shared", "-fPIC", "-w", "-I" + sysconfig.get_paths()["include"],
               "-I" + devkit, wrap, src, "-o", swig], verbose)
         shutil.copyfile(os.path.join(devkit, "polyiou.py"), os.path.join(OUT, "polyiou.py"))
+    # 2b. the DEVICE functions of the reference's CUDA-only ops, compiled as host C++.  The .cu files cannot be built as
+    #     CUDA (THC headers), but everything above their __global__ kernel is plain C++ behind `__device__`: that part is
+    #     piped to g++ (read where it lies, cut at the kernel, never written to disk) between a prefix that blanks the
+    #     CUDA qualifiers / missing headers and a C-ABI wrapper.  -ffp-contract=off: separately rounded operations.
+    _device_as_host(os.path.join(REF, "mmdet/ops/minarearect/src/minarearect_kernel.cu"), "__global__ void minareabbox_kernel",
+                    os.path.join(HERE, "ref_harness_minarearect_device.inc"), os.path.join(OUT, "ref_minarearect_dev.so"), verbose)
+    _device_as_host(os.path.join(REF, "mmdet/ops/iou/src/convex_iou_kernel.cu"), "__global__ void convex_iou_kernel",
+                    os.path.join(HERE, "ref_harness_convex_iou_device.inc"), os.path.join(OUT, "ref_convex_iou_dev.so"), verbose)
     if not with_torch:
         return OUT
     # 3./4. torch CPU extensions, reference sources unmodified

@@ -6,8 +6,9 @@
  *   mmdet/ops/iou/src/convex_iou_kernel.cu:62-137   area / lineCross / polygon_cut / intersectArea / intersectAreaO
  *   mmdet/ops/iou/src/convex_iou_kernel.cu:268-294  devrIoU: IoU(hull(9 points), quadrilateral), returned as float
  *
- * PARITY UNPINNED BY THE REFERENCE: the source is CUDA-only (includes THC/THC.h, not buildable against torch 2.11)
- * and has no CPU twin or test.  The clipping core is the polyiou algorithm whose fp64 instantiation IS pinned
+ * PINNED: the source is CUDA-only (includes THC/THC.h, not buildable as CUDA against torch 2.11) and has no CPU twin or
+ * test, but oracle/build_ref.py compiles its __device__ functions as host C++; this restatement reproduces devrIoU bit for
+ * bit (tests/golden/device_ops_ref.npz, tests/test_oracle_golden.py).  The clipping core is the polyiou algorithm whose fp64 instantiation IS pinned
  * bit-for-bit against the compiled DOTA_devkit/polyiou.cpp; the only textual difference (no fabs() on the clipped
  * triangle's area, :124-127) is selected by FAN_SIGNED_AREA.  The whole function is pinned by property: it agrees
  * with cv2.convexHull + cv2.intersectConvexConvex to 1e-6 (tests/test_oracle_golden.py).

@@ -6,10 +6,11 @@
  * gift-wrapped hull -> smallest enclosing rectangle over the hull-edge directions -> 4 corners,
  * plus the hull-vertex -> input-point index map the reference calls points_to_convex_ind.
  *
- * PARITY UNPINNED BY THE REFERENCE: the reference implementation exists only as CUDA that
- * includes THC/THC.h (not buildable against torch 2.11, and there is no CPU twin), and the
- * reference has no test for it.  This restatement is pinned instead by property tests
- * (tests/test_minarearect_oracle.py: cv2.minAreaRect area agreement, containment, analytic cases).
+ * PINNED BY THE REFERENCE'S OWN DEVICE CODE: the reference implementation exists only as CUDA that includes
+ * THC/THC.h (not buildable as CUDA against torch 2.11, no CPU twin, no test), but oracle/build_ref.py compiles its
+ * __device__ functions as host C++ and tests/golden/device_ops_ref.npz holds their outputs: hull index maps
+ * identical, rectangles identical or within 1e-6 (cos, see below) except near-ties of the min-area argmin (same area).
+ * Also pinned by properties (cv2.minAreaRect area agreement, containment, analytic cases).
  *
  * Arithmetic follows the reference's mixed precision: fp32 storage, fp64 cross products in
  * the hull (:267-270), fp64 atan2/fmod (:79-83), fp32 for the negative-angle reduction (:85-87)

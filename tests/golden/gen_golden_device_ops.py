@@ -1,0 +1,53 @@
+"""Golden vectors for the two CUDA-only geometry ops from the reference's OWN device code:
+oracle/build_ref.py compiles the __device__ functions of
+    mmdet/ops/minarearect/src/minarearect_kernel.cu   (Findminbox :343-452, Jarvis_and_index :215-341)
+    mmdet/ops/iou/src/convex_iou_kernel.cu            (devrIoU :268-294)
+as host C++ (the text above the __global__ kernels, separately rounded arithmetic); this script runs them.
+
+    python oracle/build_ref.py && python tests/golden/gen_golden_device_ops.py    # needs /root/reference
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as po                                                    # noqa: E402
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def main():
+    rm = ctypes.CDLL(os.path.join(ROOT, "oracle/_ref/ref_minarearect_dev.so"))
+    rc = ctypes.CDLL(os.path.join(ROOT, "oracle/_ref/ref_convex_iou_dev.so"))
+    rng = np.random.RandomState(0)
+    n = 6000
+    pts = rng.normal(0, 2.0, (n, 18)).astype(np.float32)
+    pts[:200, 6:] = np.tile(pts[:200, :2], (1, 6))                                  # duplicated points
+    g = np.stack(np.meshgrid(np.arange(3), np.arange(3)), -1).reshape(-1).astype(np.float32)
+    pts[200:300] = g[None] * rng.randint(1, 5, (100, 1)).astype(np.float32) + rng.randint(-5, 5, (100, 1)).astype(np.float32)
+    pts[300:400, 4:6] = (pts[300:400, 0:2] + pts[300:400, 2:4]) / 2                 # collinear triples
+    boxes = np.zeros((n, 8), np.float32)
+    rm.ref_minarearect(P(pts), n, P(boxes))
+    maps = np.full((n, 9), -1, np.int32)
+    hull_n = np.zeros(n, np.int32)
+    for i in range(n):
+        hull_n[i] = rm.ref_hull_index_map(P(pts[i]), P(maps[i]))
+    N, K = 1500, 40
+    p2 = (rng.rand(N, 9, 2) * 60 + rng.rand(N, 1, 2) * 100).astype(np.float32).reshape(N, 18)
+    p2[:100, 6:] = np.tile(p2[:100, :2], (1, 6))
+    q = po.gen_rotated_boxes(K, seed=4, extent=160.0, wmin=10, wmax=80)[:, :8].astype(np.float32)
+    iou = np.zeros((N, K), np.float32)
+    rc.ref_convex_iou(P(p2), N, P(q), K, P(iou))
+    np.savez_compressed(os.path.join(HERE, "device_ops_ref.npz"), mar_pts=pts, mar_boxes=boxes, mar_map=maps, mar_hull_n=hull_n,
+                        cx_pts=p2, cx_quads=q, cx_iou=iou)
+    print("wrote device_ops_ref.npz", boxes.shape, iou.shape)
+
+
+if __name__ == "__main__":
+    main()

@@ -9,7 +9,8 @@ repo; oracle/_ref/ is git-ignored but travels to the GPU box with the gpurun sna
   ref_rnms_cpu.so     mmdet/ops/nms/src/rnms_cpu.cpp unmodified (+ oracle/ref_harness_rnms.cpp)
   ref_box_iou_rotated.so  mmdet/ops/box_iou_rotated/src/box_iou_rotated_cpu.cpp unmodified
 
-  ref_minarearect_dev.so / ref_convex_iou_dev.so   the __device__ functions of minarearect_kernel.cu / convex_iou_kernel.cu
+  ref_minarearect_dev.so / ref_convex_iou_dev.so / ref_poly_nms_dev.so / ref_poly_overlaps_dev.so
+                      the __device__ functions of minarearect_kernel.cu / convex_iou_kernel.cu / poly_nms_kernel.cu / poly_overlaps_kernel.cu
                       compiled as HOST C++ (the text above their __global__ kernel, piped to g++; see _device_as_host)
 
 Only runs where /root/reference exists (the authoring container).  The reference's CUDA
@@ -48,7 +49,7 @@ _DEVICE_PREFIX = """
 """
 
 
-def _device_as_host(cu_path, cut_marker, wrapper_path, out_so, verbose):
+def _device_as_host(cu_path, cut_marker, wrapper_path, out_so, verbose, extra_prefix=""):
     """compile the part of a reference .cu file that precedes `cut_marker` (its __device__ functions) as host C++"""
     if not (os.path.exists(cu_path) and os.path.exists(wrapper_path)):
         return
@@ -57,7 +58,7 @@ def _device_as_host(cu_path, cut_marker, wrapper_path, out_so, verbose):
     text = open(cu_path).read()
     cut = text.index(cut_marker)
     body = "\n".join(l for l in text[:cut].splitlines() if not l.lstrip().startswith("#include"))   # ATen / THC headers
-    unit = _DEVICE_PREFIX + body + "\n" + open(wrapper_path).read()
+    unit = _DEVICE_PREFIX + extra_prefix + body + "\n" + open(wrapper_path).read()
     cmd = ["g++", "-x", "c++", "-", "-O2", "-shared", "-fPIC", "-w", "-ffp-contract=off", "-o", out_so]
     if verbose:
         print(" ".join(cmd), "  <", cu_path, "(device part) +", wrapper_path)
@@ -91,6 +92,12 @@ def build(verbose=False, with_torch=True):
                     os.path.join(HERE, "ref_harness_minarearect_device.inc"), os.path.join(OUT, "ref_minarearect_dev.so"), verbose)
     _device_as_host(os.path.join(REF, "mmdet/ops/iou/src/convex_iou_kernel.cu"), "__global__ void convex_iou_kernel",
                     os.path.join(HERE, "ref_harness_convex_iou_device.inc"), os.path.join(OUT, "ref_convex_iou_dev.so"), verbose)
+    f2 = ("struct float2 { float x, y; };\nstatic inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }\n"
+          "struct uint3_ { unsigned x, y, z; };\nstatic uint3_ blockIdx, blockDim, threadIdx;   // referenced by leftover debug code\n")
+    _device_as_host(os.path.join(devkit, "poly_nms_gpu/poly_nms_kernel.cu"), "__global__ void poly_nms_kernel",
+                    os.path.join(HERE, "ref_harness_poly_nms_device.inc"), os.path.join(OUT, "ref_poly_nms_dev.so"), verbose, f2)
+    _device_as_host(os.path.join(devkit, "poly_nms_gpu/poly_overlaps_kernel.cu"), "__global__ void overlaps_kernel",
+                    os.path.join(HERE, "ref_harness_poly_overlaps_device.inc"), os.path.join(OUT, "ref_poly_overlaps_dev.so"), verbose, f2)
     if not with_torch:
         return OUT
     # 3./4. torch CPU extensions, reference sources unmodified

@@ -2,6 +2,8 @@
 oracle/build_ref.py compiles the __device__ functions of
     mmdet/ops/minarearect/src/minarearect_kernel.cu   (Findminbox :343-452, Jarvis_and_index :215-341)
     mmdet/ops/iou/src/convex_iou_kernel.cu            (devrIoU :268-294)
+    DOTA_devkit/poly_nms_gpu/poly_nms_kernel.cu       (devPolyIoU :192-212)
+    DOTA_devkit/poly_nms_gpu/poly_overlaps_kernel.cu  (RotBox2Poly :280-297, devPolyIoU :300-328)
 as host C++ (the text above the __global__ kernels, separately rounded arithmetic); this script runs them.
 
     python oracle/build_ref.py && python tests/golden/gen_golden_device_ops.py    # needs /root/reference
@@ -44,8 +46,28 @@ def main():
     q = po.gen_rotated_boxes(K, seed=4, extent=160.0, wmin=10, wmax=80)[:, :8].astype(np.float32)
     iou = np.zeros((N, K), np.float32)
     rc.ref_convex_iou(P(p2), N, P(q), K, P(iou))
+    # DOTA_devkit/poly_nms_gpu: poly_nms_kernel.cu devPolyIoU (:192-212) on aligned quad pairs, poly_overlaps_kernel.cu
+    # devPolyIoU / RotBox2Poly (:280-328) on (cx, cy, w, h, theta) boxes
+    rn = ctypes.CDLL(os.path.join(ROOT, "oracle/_ref/ref_poly_nms_dev.so"))
+    ro = ctypes.CDLL(os.path.join(ROOT, "oracle/_ref/ref_poly_overlaps_dev.so"))
+    d = po.gen_clustered_boxes(60, 20, seed=5)
+    r2 = np.random.RandomState(1)
+    ii, jj = r2.randint(0, d.shape[0], 20000), r2.randint(0, d.shape[0], 20000)
+    pp = np.ascontiguousarray(d[ii, :8], dtype=np.float32)
+    qq = np.ascontiguousarray(d[jj, :8], dtype=np.float32)
+    pn = np.zeros(20000, np.float32)
+    rn.ref_poly_nms_iou_pairs(P(pp), P(qq), 20000, P(pn))
+    b = np.stack([r2.uniform(0, 200, 300), r2.uniform(0, 200, 300), r2.uniform(5, 60, 300), r2.uniform(5, 60, 300),
+                  r2.uniform(-3.2, 3.2, 300)], 1).astype(np.float32)
+    qb = b[:40].copy()
+    qb[:, :2] += r2.normal(0, 5, (40, 2)).astype(np.float32)
+    ov = np.zeros((300, 40), np.float32)
+    ro.ref_poly_overlaps(P(b), 300, P(qb), 40, P(ov))
+    quads = np.zeros((300, 8), np.float32)
+    ro.ref_rotbox2poly(P(b), 300, P(quads))
     np.savez_compressed(os.path.join(HERE, "device_ops_ref.npz"), mar_pts=pts, mar_boxes=boxes, mar_map=maps, mar_hull_n=hull_n,
-                        cx_pts=p2, cx_quads=q, cx_iou=iou)
+                        cx_pts=p2, cx_quads=q, cx_iou=iou, pn_p=pp, pn_q=qq, pn_iou=pn, po_boxes=b, po_query=qb, po_iou=ov,
+                        po_quads=quads)
     print("wrote device_ops_ref.npz", boxes.shape, iou.shape)
 
 

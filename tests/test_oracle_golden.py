@@ -302,3 +302,16 @@ def test_convex_iou_oracle_bit_identical_to_reference_device_code(po):
     out = po.convex_iou(g["cx_pts"], g["cx_quads"])
     assert np.array_equal(out.view(np.uint32), g["cx_iou"].view(np.uint32))
     assert (g["cx_iou"] > 0.05).mean() > 0.05
+
+
+def test_poly_nms_and_poly_overlaps_oracles_bit_identical_to_reference_device_code(po):
+    """DOTA_devkit/poly_nms_gpu has CUDA sources only; their __device__ functions compiled as host C++
+    (oracle/build_ref.py) give tests/golden/device_ops_ref.npz.  The restatements reproduce every float: devPolyIoU of
+    poly_nms_kernel.cu on 20 000 clustered quad pairs, RotBox2Poly and devPolyIoU of poly_overlaps_kernel.cu on 300 x 40
+    (cx, cy, w, h, theta) boxes."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "device_ops_ref.npz"))
+    mine = np.array([po.iou_polynms_f32_one(p, q) for p, q in zip(g["pn_p"][:4000], g["pn_q"][:4000])], dtype=np.float32)
+    assert np.array_equal(mine.view(np.uint32), g["pn_iou"][:4000].view(np.uint32))
+    assert np.array_equal(po.rotbox_to_quad_f32(g["po_boxes"]), g["po_quads"])
+    ov = po.poly_overlaps_f32(g["po_boxes"], g["po_query"])
+    assert np.array_equal(ov.view(np.uint32), g["po_iou"].view(np.uint32)) and (ov > 0).mean() > 0.1

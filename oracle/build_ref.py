@@ -11,6 +11,7 @@ repo; oracle/_ref/ is git-ignored but travels to the GPU box with the gpurun sna
 
   ref_minarearect_dev.so / ref_convex_iou_dev.so / ref_poly_nms_dev.so / ref_poly_overlaps_dev.so
                       the __device__ functions of minarearect_kernel.cu / convex_iou_kernel.cu / poly_nms_kernel.cu / poly_overlaps_kernel.cu
+  ref_dcn_dev.so      deform_conv_cuda_kernel.cu: bilinear samplers + the (modulated_)deformable_im2col KERNELS run on the host
                       compiled as HOST C++ (the text above their __global__ kernel, piped to g++; see _device_as_host)
 
 Only runs where /root/reference exists (the authoring container).  The reference's CUDA
@@ -56,8 +57,15 @@ def _device_as_host(cu_path, cut_marker, wrapper_path, out_so, verbose, extra_pr
     if not _stale(out_so, [cu_path, wrapper_path, os.path.abspath(__file__)]):
         return
     text = open(cu_path).read()
-    cut = text.index(cut_marker)
-    body = "\n".join(l for l in text[:cut].splitlines() if not l.lstrip().startswith("#include"))   # ATen / THC headers
+    if isinstance(cut_marker, str):
+        segments = [(None, cut_marker)]
+    else:
+        segments = cut_marker                       # [(start marker or None, end marker), ...]: several device-only ranges
+    part = ""
+    for a, b in segments:
+        i0 = 0 if a is None else text.index(a)
+        part += text[i0:text.index(b, i0)] + "\n"
+    body = "\n".join(l for l in part.splitlines() if not l.lstrip().startswith("#include"))   # ATen / THC headers
     unit = _DEVICE_PREFIX + extra_prefix + body + "\n" + open(wrapper_path).read()
     cmd = ["g++", "-x", "c++", "-", "-O2", "-shared", "-fPIC", "-w", "-ffp-contract=off", "-o", out_so]
     if verbose:
@@ -98,6 +106,16 @@ def build(verbose=False, with_torch=True):
                     os.path.join(HERE, "ref_harness_poly_nms_device.inc"), os.path.join(OUT, "ref_poly_nms_dev.so"), verbose, f2)
     _device_as_host(os.path.join(devkit, "poly_nms_gpu/poly_overlaps_kernel.cu"), "__global__ void overlaps_kernel",
                     os.path.join(HERE, "ref_harness_poly_overlaps_device.inc"), os.path.join(OUT, "ref_poly_overlaps_dev.so"), verbose, f2)
+    # DCN: the bilinear sampler + the im2col KERNELS themselves (their grid-stride loop macro runs the whole index range on the
+    # host once blockIdx = threadIdx = 0 and blockDim = gridDim = 1); DCNv1 range + DCNv2 (modulated) range of the file
+    cuda1 = ("namespace at {}\nstruct uint3_ { unsigned x, y, z; };\n"
+             "static uint3_ blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};\n")
+    _device_as_host(os.path.join(REF, "mmdet/ops/dcn/src/deform_conv_cuda_kernel.cu"),
+                    [(None, "void deformable_im2col("),
+                     ("template <typename scalar_t>\n__device__ scalar_t dmcn_im2col_bilinear", "template <typename scalar_t>\n__device__ scalar_t dmcn_get_gradient_weight"),
+                     ("template <typename scalar_t>\n__global__ void modulated_deformable_im2col_gpu_kernel",
+                      "template <typename scalar_t>\n__global__ void modulated_deformable_col2im_gpu_kernel")],
+                    os.path.join(HERE, "ref_harness_dcn_device.inc"), os.path.join(OUT, "ref_dcn_dev.so"), verbose, cuda1)
     if not with_torch:
         return OUT
     # 3./4. torch CPU extensions, reference sources unmodified

@@ -14,7 +14,8 @@ PINNED (the reference has no tests of its own for these layers, so its code is r
     (tests/golden/gen_golden_dense.py -> dense_ref.npz, tests/test_oracle_golden.py);
   * get_bboxes_single + multiclass_rnms: bit-identical detections / labels / order to the reference's OWN python functions
     run with the two CUDA ops replaced by their oracles (gen_golden_postprocess.py -> postprocess.npz);
-  * deform_conv_ref: the reference's DeformConv is CUDA-only (THC) - pinned against torchvision.ops.deform_conv2d.
+  * deform_conv_ref: equal (1e-15, float64) to weight x the columns of the reference's OWN (modulated_)deformable_im2col
+    kernels compiled as host C++ (oracle/build_ref.py, device_ops_ref.npz), and to torchvision.ops.deform_conv2d.
 """
 import numpy as np
 import torch

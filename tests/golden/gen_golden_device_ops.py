@@ -2,6 +2,7 @@
 oracle/build_ref.py compiles the __device__ functions of
     mmdet/ops/minarearect/src/minarearect_kernel.cu   (Findminbox :343-452, Jarvis_and_index :215-341)
     mmdet/ops/iou/src/convex_iou_kernel.cu            (devrIoU :268-294)
+    mmdet/ops/dcn/src/deform_conv_cuda_kernel.cu      ((modulated_)deformable_im2col_gpu_kernel :190-243, :570-633)
     DOTA_devkit/poly_nms_gpu/poly_nms_kernel.cu       (devPolyIoU :192-212)
     DOTA_devkit/poly_nms_gpu/poly_overlaps_kernel.cu  (RotBox2Poly :280-297, devPolyIoU :300-328)
 as host C++ (the text above the __global__ kernels, separately rounded arithmetic); this script runs them.
@@ -65,7 +66,21 @@ def main():
     ro.ref_poly_overlaps(P(b), 300, P(qb), 40, P(ov))
     quads = np.zeros((300, 8), np.float32)
     ro.ref_rotbox2poly(P(b), 300, P(quads))
-    np.savez_compressed(os.path.join(HERE, "device_ops_ref.npz"), mar_pts=pts, mar_boxes=boxes, mar_map=maps, mar_hull_n=hull_n,
+    # mmdet/ops/dcn/src/deform_conv_cuda_kernel.cu: (modulated_)deformable_im2col_gpu_kernel run on the host, float64
+    rd = ctypes.CDLL(os.path.join(ROOT, "oracle/_ref/ref_dcn_dev.so"))
+    dcn = {}
+    r3 = np.random.RandomState(7)
+    for ci, (nb, c, h, w, s_, p_, d_) in enumerate([(2, 8, 11, 13, 1, 1, 1), (1, 16, 9, 9, 2, 1, 1), (1, 4, 10, 12, 1, 2, 2), (3, 8, 7, 8, 1, 0, 1)]):
+        ho, wo = (h + 2 * p_ - 2 * d_ - 1) // s_ + 1, (w + 2 * p_ - 2 * d_ - 1) // s_ + 1
+        x = r3.randn(nb, c, h, w)
+        off = r3.randn(nb, 18, ho, wo) * 2.5                                        # many samples leave the image
+        msk = r3.rand(nb, 9, ho, wo)
+        col1, col2 = np.zeros((c * 9, nb, ho, wo)), np.zeros((c * 9, nb, ho, wo))
+        rd.ref_deformable_im2col_f64(P(x), P(off), None, nb, c, h, w, 3, 3, p_, s_, d_, P(col1))
+        rd.ref_deformable_im2col_f64(P(x), P(off), P(msk), nb, c, h, w, 3, 3, p_, s_, d_, P(col2))
+        dcn.update({"dcn%d_cfg" % ci: np.array([s_, p_, d_]), "dcn%d_x" % ci: x, "dcn%d_off" % ci: off, "dcn%d_mask" % ci: msk,
+                    "dcn%d_col" % ci: col1, "dcn%d_colm" % ci: col2})
+    np.savez_compressed(os.path.join(HERE, "device_ops_ref.npz"), **dcn, mar_pts=pts, mar_boxes=boxes, mar_map=maps, mar_hull_n=hull_n,
                         cx_pts=p2, cx_quads=q, cx_iou=iou, pn_p=pp, pn_q=qq, pn_iou=pn, po_boxes=b, po_query=qb, po_iou=ov,
                         po_quads=quads)
     print("wrote device_ops_ref.npz", boxes.shape, iou.shape)

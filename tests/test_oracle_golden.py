@@ -315,3 +315,23 @@ def test_poly_nms_and_poly_overlaps_oracles_bit_identical_to_reference_device_co
     assert np.array_equal(po.rotbox_to_quad_f32(g["po_boxes"]), g["po_quads"])
     ov = po.poly_overlaps_f32(g["po_boxes"], g["po_query"])
     assert np.array_equal(ov.view(np.uint32), g["po_iou"].view(np.uint32)) and (ov > 0).mean() > 0.1
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_dcn_oracle_vs_reference_im2col_kernels(case):
+    """tests/golden/device_ops_ref.npz holds the column matrices the reference's OWN
+    deformable_im2col_gpu_kernel / modulated_deformable_im2col_gpu_kernel (deform_conv_cuda_kernel.cu:190-243, :570-633)
+    produce when their text is compiled as host C++ (float64; stride / padding / dilation variants, offsets leaving the
+    image, DCNv2 mask).  weight x columns (the GEMM of deform_conv_cuda.cpp:231-236) equals the oracle's deform_conv_ref."""
+    import torch
+    from oracle import torch_reference as tr
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "device_ops_ref.npz"))
+    s_, p_, d_ = [int(v) for v in g["dcn%d_cfg" % case]]
+    x, off, msk = (torch.from_numpy(g["dcn%d_%s" % (case, k)]) for k in ("x", "off", "mask"))
+    n, c = x.shape[0], x.shape[1]
+    wt = torch.randn(5, c, 3, 3, generator=torch.Generator().manual_seed(case), dtype=torch.float64)
+    for key, mask in (("col", None), ("colm", msk)):
+        col = g["dcn%d_%s" % (case, key)]
+        ref = (wt.numpy().reshape(5, c * 9) @ col.reshape(c * 9, -1)).reshape(5, n, col.shape[2], col.shape[3]).transpose(1, 0, 2, 3)
+        mine = tr.deform_conv_ref(x, off, wt, s_, p_, d_, mask=mask).numpy()
+        assert mine.shape == ref.shape and np.abs(mine - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())

@@ -245,6 +245,8 @@ typedef struct {
     double *gn_stats;           /* optional: double [N,32,2] (sum, sum of squares) of the bf16 output,
                                    zeroed by the caller - the GroupNorm(32) statistics of the layer,
                                    accumulated in the convolution's epilogue when the shape allows    */
+    const float *mask;          /* deformable only, optional DCNv2 modulation: fp32 [N,Ho,Wo,KH*KW]
+                                   (modulated_deformable_im2col_gpu_kernel, deform_conv_cuda_kernel.cu:570-633) */
 } orp_tc_problem;
 
 /* y = relu?(conv(x, w) + bias + residual) for up to 5 problems sharing the weights.  deform != 0:
@@ -253,6 +255,38 @@ typedef struct {
 int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const void *w, int Cout, int Cout_padded,
                     int KH, int KW, int Cin, int stride, int pad, const float *bias, int relu, int out_f32,
                     int deform, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The same layers in f16x3 ("split") arithmetic - the PARITY mode of the tensor-core engine.  The
+ * reference computes nn.Conv2d / DeformConv in fp32 (resnet.py:203-239, fpn.py:138-178,
+ * orientedreppoints_head.py:148-171; torch 1.4: no TF32).  Here every fp32 value travels as an fp16
+ * pair x = hi + lo (hi = fp16(x), lo = fp16(x - hi): 22 significand bits) and every product is
+ * hi*hi + lo*hi + hi*lo: three tcgen05 MMAs into one fp32 TMEM accumulator (dropped lo*lo term 2^-22).
+ * Activations: fp16 [N,H,W,2,C] (per pixel: C hi values, then C lo values).  Weights: fp16
+ * [Cout_padded][KH*KW][2][Cin_padded to 64] holding (hi, lo) of w * 2^wscale_log2 - the power-of-two
+ * scale (0..15, chosen by the caller so the scaled weights have rms ~ 1) keeps the lo halves out of the
+ * fp16 subnormal range; the epilogue multiplies by 2^-wscale_log2 (exact) before bias / activation.
+ * Same orp_tc_problem: x / out / residual_bf16 point at split tensors; out_f32 outputs are plain fp32.
+ * Outputs beyond +-65504 are saturated and counted (orp_f16x3_overflow_count).
+ * ---------------------------------------------------------------------------------------- */
+int orp_conv2d_f16x3(int nprob, const orp_tc_problem *probs, const void *w_split, int Cout, int Cout_padded,
+                     int KH, int KW, int Cin, int stride, int pad, const float *bias, int wscale_log2, int relu,
+                     int out_f32, int deform, void *stream);
+/* number of tile rows that saturated since the last reset (host-blocking read of a device counter) */
+int orp_f16x3_overflow_count(unsigned int *count, int reset);
+/* stem in split form: space-to-depth planes fp16 [2][N, H/2+3, W/2+3, 16] (hi plane, lo plane) from the uint8 HWC
+ * tiles (Normalize fused) or the NCHW fp32 image, conv1 as a 4x4 stride-1 convolution over them */
+int orp_stem_s2d_u8_f16x3(const uint8_t *img_hwc, int N, int H, int W, const float *mean, const float *std, int to_rgb,
+                          void *out, void *stream);
+int orp_stem_s2d_f16x3(const float *img_nchw, int N, int H, int W, void *out, void *stream);
+int orp_stem_conv_s2d_f16x3(const void *x_s2d, int N, int H, int W, const void *w_split, const float *bias,
+                            int wscale_log2, int relu, void *out, void *stream);
+/* memory-bound companions on split tensors [N,H,W,2,C] */
+int orp_maxpool3x3s2_f16x3(const void *x, int N, int H, int W, int C, void *y, void *stream);
+int orp_gn_stats_f16x3(const void *x, int N, int HW, int C, int groups, double *stats, void *stream);
+/* fp32 NHWC [N,H,W,C] <-> split fp16 [N,H,W,2,C] (boundary conversions: DeformConv operator surface, tests) */
+int orp_split_from_f32(const float *x, long long pixels, int C, void *y_split, void *stream);
+int orp_split_to_f32(const void *x_split, long long pixels, int C, float *y, void *stream);
 
 /* conv1 of the ResNet stem (7x7, stride 2, pad 3, 3 channels; resnet.py:495) + folded BN + ReLU straight
  * from the NCHW fp32 image: the im2col rows (k = (kh*7+kw)*3 + c, K padded 147 -> 192) are built in shared
@@ -284,7 +318,7 @@ int orp_gn_apply_bf16(const void *x, int N, int H, int W, int C, const double *s
  * orientedreppoints_head.py:175-190) in one launch.  up_src (optional, [N,(H+1)/2,(W+1)/2,256]) is added after the
  * normalisation with nearest-neighbour upsampling (the FPN top-down path, fpn.py:171-176). */
 typedef struct orp_gn_problem {
-    const void *x;        /* bf16 NHWC [N,H,W,256] */
+    const void *x;        /* bf16 NHWC [N,H,W,256] (split fp16 [N,H,W,2,256] for the f16x3 entry point) */
     int N, H, W;
     const double *stats;  /* [N,32,2] sums / sums of squares */
     const void *up_src;   /* optional */
@@ -292,6 +326,9 @@ typedef struct orp_gn_problem {
 } orp_gn_problem;
 int orp_gn_apply_bf16_multi(int nprob, const orp_gn_problem *probs, int C, int groups, const float *gamma,
                             const float *beta, float eps, int relu, void *stream);
+/* the same on split fp16 tensors [N,H,W,2,256] (f16x3 engine) */
+int orp_gn_apply_f16x3_multi(int nprob, const orp_gn_problem *probs, int C, int groups, const float *gamma,
+                             const float *beta, float eps, int relu, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Tile producer (DOTA_devkit/SplitOnlyImage_multi_process.py:38-49 saveimagepatches): cut ntiles windows of

@@ -30,7 +30,7 @@ class NmsStats(ctypes.Structure):
 
 class TcProblem(ctypes.Structure):
     _fields_ = [("x", _vp), ("N", _i), ("H", _i), ("W", _i), ("out", _vp), ("residual_bf16", _vp),
-                ("residual_f32", _vp), ("offset", _vp), ("gn_stats", _vp)]
+                ("residual_f32", _vp), ("offset", _vp), ("gn_stats", _vp), ("mask", _vp)]
 
 
 class GnProblem(ctypes.Structure):
@@ -62,6 +62,16 @@ SIGNATURES = {
     "orp_gn_apply_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _f, _i, _vp, _vp, _vp]),
     "orp_maxpool3x3s2_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "orp_conv2d_bf16": (_i, [_i, ctypes.POINTER(TcProblem), _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    "orp_conv2d_f16x3": (_i, [_i, ctypes.POINTER(TcProblem), _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
+    "orp_f16x3_overflow_count": (_i, [ctypes.POINTER(ctypes.c_uint), _i]),
+    "orp_stem_s2d_u8_f16x3": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "orp_stem_s2d_f16x3": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "orp_stem_conv_s2d_f16x3": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    "orp_maxpool3x3s2_f16x3": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "orp_gn_stats_f16x3": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "orp_gn_apply_f16x3_multi": (_i, [_i, _vp, _i, _i, _vp, _vp, _f, _i, _vp]),
+    "orp_split_from_f32": (_i, [_vp, ctypes.c_longlong, _i, _vp, _vp]),
+    "orp_split_to_f32": (_i, [_vp, ctypes.c_longlong, _i, _vp, _vp]),
     "orp_layernorm_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _i, _vp, _vp]),
     "orp_window_attention_bf16": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _vp, _vp]),
     "orp_patch_embed_rows_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp]),

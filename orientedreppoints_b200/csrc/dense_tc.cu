@@ -22,8 +22,16 @@
 //               bilinear sample of the reference (deform_conv_cuda_kernel.cu:84-115) is computed in
 //               fp32 from bf16 features and written to shared memory in the same swizzled layout.
 // Several "problems" (the five FPN levels, which share the head weights) are served by ONE launch.
+//
+// Two operand modes share the kernel.  bf16: activations / weights rounded to bf16, one MMA per K step.
+// f16x3 ("split"): every fp32 value is carried as an fp16 pair x = hi + lo (22 significand bits, activations
+// stored [N,H,W,2,C]: hi channels then lo channels per pixel) and every product is evaluated as
+// hi*hi + lo*hi + hi*lo with three MMAs into the same fp32 TMEM accumulator (the dropped lo*lo term is 2^-22
+// relative) - fp32-faithful arithmetic at 1/3 of the tensor-pipe rate; this is the parity mode.  The K loop
+// simply runs three "terms" per (tap, channel block); weights are stored [Cout][tap][2][Cin] = (hi, lo).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 #include <mutex>
@@ -61,11 +69,12 @@ struct Problem {
     int BW, BH, BI;                           // tile box: BW*BH*BI == 128 output pixels (powers of two)
     int lbw, lbh;                             // log2(BW), log2(BH)
     int tiles_w, tiles_h, tiles_i, tile_start;
-    void *out;                                // bf16 or fp32 NHWC [N,Ho,Wo,Cout]
-    const __nv_bfloat16 *res;                 // optional residual, bf16 NHWC [N,Ho,Wo,Cout]
+    void *out;                                // bf16 / split-fp16 or fp32 NHWC [N,Ho,Wo,(2,)Cout]
+    const __nv_bfloat16 *res;                 // optional residual, same layout as the 16-bit output
     const float *res32;                       // optional fp32 residual (head: refine += init)
-    const __nv_bfloat16 *x;                   // activation base (deformable variant)
+    const __nv_bfloat16 *x;                   // activation base (deformable variant; fp16 pairs in split mode)
     const float *offset;                      // deformable: [N,Ho,Wo,2*taps] fp32
+    const float *mask;                        // deformable, optional DCNv2 modulation: [N,Ho,Wo,taps] fp32
     double *gn_stats;                         // optional [N, 32, 2] (sum, sum of squares) of the output, GroupNorm(32)
 };
 
@@ -83,6 +92,9 @@ struct alignas(64) TcParams {
     int gn_fused;                             // GroupNorm statistics accumulated in the TMA epilogue (Cout == 256)
     int stem;                                 // producers build conv1's 7x7/2 im2col rows from the NCHW fp32 image
     int s2d_stem;                             // conv1 in space-to-depth form (host bookkeeping: 147 useful K of 256)
+    int split;                                // f16x3 mode: fp16 (hi, lo) operand pairs, three MMA terms per K block
+    float oscale;                             // epilogue multiplier 2^-s undoing the power-of-two weight scale (split mode)
+    unsigned int *ovf;                        // split mode: count of outputs beyond the fp16 range (saturated)
     int nprob, num_m_tiles, n_tiles_n, num_tiles;
     FastDiv fd_ntn;                           // / n_tiles_n
     int KH, KW, Cin, cin_blocks, stride, pad, Cout, relu;
@@ -132,6 +144,12 @@ __device__ __forceinline__ void tma_load_4d(void *smem, const CUtensorMap *tm, u
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(smem)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void *smem, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2, int c3, int c4)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void *smem, const CUtensorMap *tm, uint64_t *bar, int c0, int c1)
 {
@@ -234,6 +252,28 @@ struct Ring {
     __device__ void next() { if (++stage == n) { stage = 0; phase ^= 1; } }
 };
 
+// Walk of the main-loop K blocks of one tile: (tap, term, channel block).
+//   bf16:                     tap-major, one term.
+//   split, TMA operands:      the cross terms (1: x_lo * w_hi, 2: x_hi * w_lo) of ALL taps first, then the main terms
+//                             (0: x_hi * w_hi).  The tensor core truncates its fp32 accumulator on every K step (measured:
+//                             error grows linearly with the step count, 6e-6 of max at 432 steps); while only the 2^-11
+//                             times smaller cross terms have been added the accumulator's ulp - hence that loss - is 2^-11
+//                             times smaller too, so the loss of a tile is that of K/16 steps instead of 3K/16.
+//   split, deformable:        (tap, channel block, term): the producers sample once and fill three stages back to back.
+struct KIter {
+    int tap = 0, term, cb = 0, phase = 0;
+    int taps, cbn, mode;                                   // mode 0: bf16, 1: split TMA, 2: split deformable
+    __device__ KIter(int taps_, int cbn_, int mode_) : taps(taps_), cbn(cbn_), mode(mode_) { term = (mode == 1) ? 1 : 0; }
+    __device__ void next()
+    {
+        if (mode == 0) { if (++cb == cbn) { cb = 0; ++tap; } }
+        else if (mode == 2) { if (++term == 3) { term = 0; if (++cb == cbn) { cb = 0; ++tap; } } }
+        else if (phase == 0) {
+            if (++cb == cbn) { cb = 0; if (++term == 3) { term = 1; if (++tap == taps) { tap = 0; term = 0; phase = 1; } } }
+        } else { if (++cb == cbn) { cb = 0; ++tap; } }
+    }
+};
+
 __device__ __forceinline__ void decode_tile(const TcParams &P, int tile, int &pi, int &wb, int &hb, int &ib, int &nt)
 {
     uint32_t mt_u, nt_u;
@@ -261,6 +301,18 @@ constexpr IdentBlock make_ident()
     return b;
 }
 __device__ IdentBlock g_ident = make_ident();
+// split mode: 2^s * identity in fp16 for s = 0..15 (the weights of a layer carry a power-of-two scale 2^s that
+// the epilogue removes, so the residual has to enter the accumulator scaled alike)
+struct IdentBlocks16 { unsigned short v[16][64 * 64]; };
+constexpr IdentBlocks16 make_ident16()
+{
+    IdentBlocks16 b{};
+    for (int s = 0; s < 16; ++s)
+        for (int i = 0; i < 64; ++i) b.v[s][i * 64 + i] = (unsigned short)((15 + s) << 10);   // fp16 2^s
+    return b;
+}
+__device__ IdentBlocks16 g_ident16 = make_ident16();
+__device__ unsigned int g_f16_overflow = 0;
 
 // ----------------------------------------------------------------------------------------------- kernel
 // BN: accumulator width (32..256).  OUT_F32: fp32 output (head predictions) instead of bf16.
@@ -280,7 +332,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     constexpr int kBBytes = BN * kBK * 2;
     // b_resident: [B slab: kblocks x kBBytes] then A-only stages; otherwise every stage carries A | B
     const int kStageBytes = P.b_resident ? kABytes : kABytes + kBBytes;
-    const int kblocks_all = P.KH * P.KW * P.cin_blocks;
+    const int kblocks_all = P.KH * P.KW * P.cin_blocks * (P.split ? 2 : 1);   // weight K blocks (hi and lo halves in split mode)
     uint8_t *ident = smem;                             // [8 KiB] identity block when res_mma
     if (P.res_mma) smem += 8192;
     uint8_t *bres = smem;
@@ -325,7 +377,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int kblocks = P.KH * P.KW * P.cin_blocks;
+    const int kblocks = P.KH * P.KW * P.cin_blocks * (P.split ? 3 : 1);       // main-loop K blocks per tile
     // Programmatic dependent launch: the next kernel in the stream may start its CTAs (barrier init, TMEM allocation,
     // descriptor prefetch - the code above) on SMs this grid has already left; nothing above touches global memory,
     // and everything below (loads AND stores) comes after the wait for the preceding grid to complete and flush.
@@ -339,47 +391,54 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
             if ((P.b_resident || P.res_mma) && (int)blockIdx.x < P.num_tiles) {
                 // gridDim.x is a multiple of n_tiles_n, so every tile of this CTA has the same N tile
                 const int nt0 = blockIdx.x % P.n_tiles_n;
-                mbar_expect_tx(&bres_bar, (uint32_t)((P.b_resident ? kblocks_all * kBBytes : 0) + (P.res_mma ? 8192 : 0)));
+                mbar_expect_tx(&bres_bar, (uint32_t)((P.b_resident ? kblocks_all * kBBytes : 0) + (P.res_mma ? 8192 : 0)));   // kblocks_all counts weight blocks
                 if (P.res_mma) tma_load_2d(ident, &P.tmI, &bres_bar, 0, 0);
                 if (P.b_resident)
                     for (int kb = 0; kb < kblocks_all; ++kb)
                         tma_load_2d(bres + (size_t)kb * kBBytes, &P.tmB, &bres_bar, kb * kBK, nt0 * BN);
             }
+            const int wterms = P.split ? 2 : 1, rterms = P.split ? 2 : 1;
             for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
                 int pi, wb, hb, ib, nt;
                 decode_tile(P, tile, pi, wb, hb, ib, nt);
                 const Problem &pr = P.prob[pi];
                 const int w0 = wb * pr.BW * P.stride - P.pad, h0 = hb * pr.BH * P.stride - P.pad, i0 = ib * pr.BI;
-                for (int tap = 0; tap < P.KH * P.KW; ++tap) {
-                    const int kh = tap / P.KW, kw = tap - kh * P.KW;
-                    for (int cb = 0; cb < P.cin_blocks; ++cb) {
-                        mbar_wait(&empty[r.stage], r.phase ^ 1);
-                        uint8_t *sa = smem + (size_t)r.stage * kStageBytes;
-                        mbar_expect_tx(&full[r.stage], DEFORM ? kBBytes : (P.b_resident ? kABytes : kABytes + kBBytes));
-                        if (!DEFORM) tma_load_4d(sa, &P.tmA[pi], &full[r.stage], cb * kBK, w0 + kw, h0 + kh, i0);
-                        if (!P.b_resident) tma_load_2d(sa + kABytes, &P.tmB, &full[r.stage], (tap * P.cin_blocks + cb) * kBK, nt * BN);
-                        r.next();
-                    }
+                KIter it(P.KH * P.KW, P.cin_blocks, P.split ? (DEFORM ? 2 : 1) : 0);
+                for (int j = 0; j < kblocks; ++j, it.next()) {
+                    const int kh = it.tap / P.KW, kw = it.tap - kh * P.KW;
+                    mbar_wait(&empty[r.stage], r.phase ^ 1);
+                    uint8_t *sa = smem + (size_t)r.stage * kStageBytes;
+                    mbar_expect_tx(&full[r.stage], DEFORM ? kBBytes : (P.b_resident ? kABytes : kABytes + kBBytes));
+                    if (!DEFORM) tma_load_5d(sa, &P.tmA[pi], &full[r.stage], it.cb * kBK, it.term == 1 ? 1 : 0, w0 + kw, h0 + kh, i0);
+                    if (!P.b_resident)
+                        tma_load_2d(sa + kABytes, &P.tmB, &full[r.stage],
+                                    ((it.tap * wterms + (it.term == 2 ? 1 : 0)) * P.cin_blocks + it.cb) * kBK, nt * BN);
+                    r.next();
                 }
                 if (!DEFORM && P.res_mma) {
-                    // residual: one extra K block per 64 output channels, the A operand is the residual tile itself
-                    for (int g = 0; g < BN / 64 && nt * BN + g * 64 < P.Cout; ++g) {
-                        mbar_wait(&empty[r.stage], r.phase ^ 1);
-                        mbar_expect_tx(&full[r.stage], kABytes);
-                        tma_load_4d(smem + (size_t)r.stage * kStageBytes, &P.tmRes[pi], &full[r.stage], nt * BN + g * 64,
-                                    wb * pr.BW, hb * pr.BH, ib * pr.BI);
-                        r.next();
-                    }
+                    // residual: one extra K block per 64 output channels (two in split mode: hi and lo), the A operand
+                    // is the residual tile itself
+                    for (int g = 0; g < BN / 64 && nt * BN + g * 64 < P.Cout; ++g)
+                        for (int t = 0; t < rterms; ++t) {
+                            mbar_wait(&empty[r.stage], r.phase ^ 1);
+                            mbar_expect_tx(&full[r.stage], kABytes);
+                            tma_load_5d(smem + (size_t)r.stage * kStageBytes, &P.tmRes[pi], &full[r.stage], nt * BN + g * 64, t,
+                                        wb * pr.BW, hb * pr.BH, ib * pr.BI);
+                            r.next();
+                        }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        // instruction descriptor: D fp32 (bit 4), A/B format (bits 7-9 / 10-12: 0 = fp16, 1 = bf16), N >> 3, M >> 4
+        const uint32_t fmt = P.split ? 0u : 1u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        const uint32_t idesc64 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
         Ring r(stages);
         int acc = 0;
         uint32_t acc_phase = 0;
-        constexpr uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        const int wterms = P.split ? 2 : 1, rterms = P.split ? 2 : 1;
         if ((P.b_resident || P.res_mma) && (int)blockIdx.x < P.num_tiles) mbar_wait(&bres_bar, 0);
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
             int res_groups = 0;
@@ -390,13 +449,15 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
             mbar_wait(&tempty[acc], acc_phase ^ 1);
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-            for (int kb = 0; kb < kblocks; ++kb) {
+            KIter it(P.KH * P.KW, P.cin_blocks, P.split ? (DEFORM ? 2 : 1) : 0);   // same walk as the producer (resident weights: slab index)
+            for (int kb = 0; kb < kblocks; ++kb, it.next()) {
                 mbar_wait(&full[r.stage], r.phase);
                 tcgen05_fence_after();
                 if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + (size_t)r.stage * kStageBytes);
                     const uint64_t da = make_desc_sw128(sa);
-                    const uint64_t db = make_desc_sw128(P.b_resident ? smem_u32(bres + (size_t)kb * kBBytes) : sa + kABytes);
+                    const int slab = (it.tap * wterms + (it.term == 2 ? 1 : 0)) * P.cin_blocks + it.cb;
+                    const uint64_t db = make_desc_sw128(P.b_resident ? smem_u32(bres + (size_t)slab * kBBytes) : sa + kABytes);
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k)
                         umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
@@ -406,8 +467,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 __syncwarp();
                 r.next();
             }
-            for (int g = 0; g < res_groups; ++g) {
-                // accumulator columns [64 g, 64 g + 64) += residual tile * identity
+            for (int g = 0; g < res_groups * rterms; ++g) {
+                // accumulator columns [64 g, 64 g + 64) += residual tile * (scaled) identity
                 mbar_wait(&full[r.stage], r.phase);
                 tcgen05_fence_after();
                 if (elect_one()) {
@@ -415,9 +476,9 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                     const uint64_t db = make_desc_sw128(smem_u32(ident));
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k)
-                        umma_bf16(d_tmem + (uint32_t)(g * 64), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc64, 1u);
+                        umma_bf16(d_tmem + (uint32_t)((g / rterms) * 64), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc64, 1u);
                     umma_commit(&empty[r.stage]);
-                    if (g == res_groups - 1) umma_commit(&tfull[acc]);
+                    if (g == res_groups * rterms - 1) umma_commit(&tfull[acc]);
                 }
                 __syncwarp();
                 r.next();
@@ -472,9 +533,9 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                         const float *rp = pr.res32 ? pr.res32 + pix * P.Cout + c0 : nullptr;
                         for (int j = 0; j < 32; ++j) {
                             if (c0 + j >= P.Cout) break;
-                            float f = __uint_as_float(v[j]);
+                            float f = __uint_as_float(v[j]) * P.oscale;
                             if (P.bias) f += P.bias[c0 + j];
-                            if (pr.res) f += __bfloat162float(pr.res[pix * P.Cout + c0 + j]);
+                            if (pr.res && !P.split) f += __bfloat162float(pr.res[pix * P.Cout + c0 + j]);
                             if (rp) f += rp[j];
                             f = act_fn(f, P.relu);
                             op[j] = f;
@@ -490,19 +551,22 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 const uint32_t bias_u = smem_u32(s_bias);
                 const bool io = (et == 0);
                 constexpr int kPasses = BN / 64;
+                const int oterms = P.split ? 2 : 1;                      // split mode: a hi pass and a lo pass per 64 columns
                 if (nt != bias_nt) {                                     // bias slice changes only with the N tile
                     bar_sync(bar_a, nthr);                               // previous tile's bias reads are done
                     for (int c = et; c < BN; c += nthr) s_bias[c] = (P.bias && nt * BN + c < P.Cout) ? P.bias[nt * BN + c] : 0.f;
                     bias_nt = nt;
                 }
+                float amax = 0.f;
 #pragma unroll 1
-                for (int half = 0; half < kPasses; ++half) {
+                for (int pass = 0; pass < kPasses * oterms; ++pass) {
+                    const int half = P.split ? (pass >> 1) : pass, oterm = P.split ? (pass & 1) : 0;
                     if (io) {
                         if (P.epi_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     }
                     bar_sync(bar_a, nthr);                               // staging buffer `ob` is free, bias staged
-                    if (half == 0) {
+                    if (pass == 0) {
                         mbar_wait(&tfull[acc], acc_phase);
                         tcgen05_fence_after();
                     }
@@ -525,6 +589,10 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
 #pragma unroll
                             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j4 * 8 + j]);
                             const uint4 b0 = bu[2 * j4], b1 = bu[2 * j4 + 1];
+                            if (P.split) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] *= P.oscale;      // exact: power of two
+                            }
                             f[0] += __uint_as_float(b0.x); f[1] += __uint_as_float(b0.y);
                             f[2] += __uint_as_float(b0.z); f[3] += __uint_as_float(b0.w);
                             f[4] += __uint_as_float(b1.x); f[5] += __uint_as_float(b1.y);
@@ -534,15 +602,35 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                                 for (int j = 0; j < 8; ++j) f[j] = act_fn(f[j], 2);
                             }
                             uint32_t pk[4];
+                            if (P.split) {
+                                // x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significand bits
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-                                // ReLU after rounding: rounding is monotone and keeps the sign, so the result is the same
-                                if (P.relu == 1) b2 = __hmax2(b2, __floats2bfloat162_rn(0.f, 0.f));
-                                pk[k] = *reinterpret_cast<uint32_t *>(&b2);
+                                for (int j = 0; j < 8; ++j) {
+                                    if (P.relu == 1) f[j] = fmaxf(f[j], 0.f);
+                                    amax = fmaxf(amax, fabsf(f[j]));
+                                    f[j] = fminf(fmaxf(f[j], -65504.f), 65504.f);
+                                }
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const __half2 h2 = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+                                    __half2 o2 = h2;
+                                    if (oterm) {
+                                        const float2 hf = __half22float2(h2);
+                                        o2 = __floats2half2_rn(f[2 * k] - hf.x, f[2 * k + 1] - hf.y);
+                                    }
+                                    pk[k] = *reinterpret_cast<const uint32_t *>(&o2);
+                                }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                                    // ReLU after rounding: rounding is monotone and keeps the sign, so the result is the same
+                                    if (P.relu == 1) b2 = __hmax2(b2, __floats2bfloat162_rn(0.f, 0.f));
+                                    pk[k] = *reinterpret_cast<uint32_t *>(&b2);
+                                }
                             }
                             sts128(orow + sw, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-                            if (P.gn_fused) {
+                            if (P.gn_fused && oterm == 0) {
                                 // one 16-byte chunk = 8 channels = one GroupNorm group (Cout 256 / 32 groups)
                                 float gs = 0.f, gq = 0.f;
                                 if (valid) {
@@ -558,7 +646,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             }
                         }
                     }
-                    if (P.gn_fused && lane < 8 && (chs == 1 || (lane >> 2) == wg)) {
+                    if (P.gn_fused && oterm == 0 && lane < 8 && (chs == 1 || (lane >> 2) == wg)) {
                         // the 32 rows of a warp belong to one image (host guarantees BW*BH >= 32)
                         const int n_img = ib * pr.BI + ((q * 32) >> (pr.lbw + pr.lbh));
                         if (n_img < pr.N) {
@@ -571,13 +659,14 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                     bar_sync(bar_b, nthr);                               // staging written by all
                     if (io) {
                         asm volatile(
-                            "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                            ::"l"(&P.tmOut[pi]), "r"(obuf_u + (uint32_t)ob * 16384u), "r"(nt * BN + half * 64),
+                            "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                            ::"l"(&P.tmOut[pi]), "r"(obuf_u + (uint32_t)ob * 16384u), "r"(nt * BN + half * 64), "r"(oterm),
                               "r"(wb * pr.BW), "r"(hb * pr.BH), "r"(ib * pr.BI) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     if (++ob == P.epi_bufs) ob = 0;
                 }
+                if (P.split && valid && amax > 65504.f) atomicAdd(P.ovf, 1u);
             } else {
                 // bf16 outputs: residual tile prefetched into shared memory with coalesced cp.async while the
                 // MMA is still running, results written back to the same staging tile, then stored coalesced
@@ -779,9 +868,13 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 w = wb * pr.BW + iw; h = hb * pr.BH + ih; n = ib * pr.BI + ii;
                 valid = (w < pr.Wo) && (h < pr.Ho) && (n < pr.N);
             }
-            const float *offp = pr.offset + (((size_t)(valid ? n : 0) * pr.Ho + (valid ? h : 0)) * pr.Wo + (valid ? w : 0)) * (2 * P.KH * P.KW);
-            const int img0 = (valid ? n : 0) * pr.H * pr.W * P.Cin;
-            for (int tap = 0; tap < P.KH * P.KW; ++tap) {
+            const int taps = P.KH * P.KW;
+            const size_t opix = ((size_t)(valid ? n : 0) * pr.Ho + (valid ? h : 0)) * pr.Wo + (valid ? w : 0);
+            const float *offp = pr.offset + opix * (2 * taps);
+            const float *mskp = pr.mask ? pr.mask + opix * taps : nullptr;
+            const int cpp = P.Cin * (P.split ? 2 : 1);                  // 16-bit elements per pixel (hi and lo halves in split mode)
+            const int img0 = (valid ? n : 0) * pr.H * pr.W * cpp;
+            for (int tap = 0; tap < taps; ++tap) {
                 if (pt < 128) {
                     const int kh = tap / P.KW, kw = tap - kh * P.KW;
                     float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -793,10 +886,16 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
                             const int h_high = h_low + 1, w_high = w_low + 1;
                             const float lh = h_im - (float)h_low, lw = w_im - (float)w_low, hh = 1.f - lh, hw = 1.f - lw;
-                            if (h_low >= 0 && w_low >= 0) { wv.x = hh * hw; ov.x = img0 + (h_low * pr.W + w_low) * P.Cin; }
-                            if (h_low >= 0 && w_high <= pr.W - 1) { wv.y = hh * lw; ov.y = img0 + (h_low * pr.W + w_high) * P.Cin; }
-                            if (h_high <= pr.H - 1 && w_low >= 0) { wv.z = lh * hw; ov.z = img0 + (h_high * pr.W + w_low) * P.Cin; }
-                            if (h_high <= pr.H - 1 && w_high <= pr.W - 1) { wv.w = lh * lw; ov.w = img0 + (h_high * pr.W + w_high) * P.Cin; }
+                            if (h_low >= 0 && w_low >= 0) { wv.x = hh * hw; ov.x = img0 + (h_low * pr.W + w_low) * cpp; }
+                            if (h_low >= 0 && w_high <= pr.W - 1) { wv.y = hh * lw; ov.y = img0 + (h_low * pr.W + w_high) * cpp; }
+                            if (h_high <= pr.H - 1 && w_low >= 0) { wv.z = lh * hw; ov.z = img0 + (h_high * pr.W + w_low) * cpp; }
+                            if (h_high <= pr.H - 1 && w_high <= pr.W - 1) { wv.w = lh * lw; ov.w = img0 + (h_high * pr.W + w_high) * cpp; }
+                            if (mskp) {
+                                // DCNv2 (modulated_deformable_im2col_gpu_kernel, deform_conv_cuda_kernel.cu:570-633): the sample
+                                // is multiplied by the mask value of (pixel, tap); folded into the four corner weights
+                                const float m = mskp[tap];
+                                wv.x *= m; wv.y *= m; wv.z *= m; wv.w *= m;
+                            }
                         }
                     }
                     s_w[tb][pt] = wv;
@@ -804,44 +903,107 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 for (int cb = 0; cb < P.cin_blocks; ++cb) {
-                    mbar_wait(&empty[r.stage], r.phase ^ 1);
-                    uint8_t *sa = smem + (size_t)r.stage * kStageBytes;
-                    uint4 u[4][4];
+                    if (!P.split) {
+                        mbar_wait(&empty[r.stage], r.phase ^ 1);
+                        uint8_t *sa = smem + (size_t)r.stage * kStageBytes;
+                        uint4 u[4][4];
 #pragma unroll
-                    for (int it = 0; it < 4; ++it) {
-                        const int item = pt + it * 256, row = item >> 3, c16 = item & 7;
-                        const int4 ov = s_o[tb][row];
-                        const int co = cb * kBK + c16 * 8;
-                        u[it][0] = *reinterpret_cast<const uint4 *>(pr.x + ov.x + co);
-                        u[it][1] = *reinterpret_cast<const uint4 *>(pr.x + ov.y + co);
-                        u[it][2] = *reinterpret_cast<const uint4 *>(pr.x + ov.z + co);
-                        u[it][3] = *reinterpret_cast<const uint4 *>(pr.x + ov.w + co);
-                    }
-#pragma unroll
-                    for (int it = 0; it < 4; ++it) {
-                        const int item = pt + it * 256, row = item >> 3, c16 = item & 7;
-                        const float4 wv = s_w[tb][row];
-                        const uint32_t *a1 = reinterpret_cast<const uint32_t *>(&u[it][0]);
-                        const uint32_t *a2 = reinterpret_cast<const uint32_t *>(&u[it][1]);
-                        const uint32_t *a3 = reinterpret_cast<const uint32_t *>(&u[it][2]);
-                        const uint32_t *a4 = reinterpret_cast<const uint32_t *>(&u[it][3]);
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a1[k]));
-                            const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a2[k]));
-                            const float2 f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a3[k]));
-                            const float2 f4 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a4[k]));
-                            const float vx = wv.x * f1.x + wv.y * f2.x + wv.z * f3.x + wv.w * f4.x;
-                            const float vy = wv.x * f1.y + wv.y * f2.y + wv.z * f3.y + wv.w * f4.y;
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(vx, vy);
-                            pk[k] = *reinterpret_cast<uint32_t *>(&b2);
+                        for (int it = 0; it < 4; ++it) {
+                            const int item = pt + it * 256, row = item >> 3, c16 = item & 7;
+                            const int4 ov = s_o[tb][row];
+                            const int co = cb * kBK + c16 * 8;
+                            u[it][0] = *reinterpret_cast<const uint4 *>(pr.x + ov.x + co);
+                            u[it][1] = *reinterpret_cast<const uint4 *>(pr.x + ov.y + co);
+                            u[it][2] = *reinterpret_cast<const uint4 *>(pr.x + ov.z + co);
+                            u[it][3] = *reinterpret_cast<const uint4 *>(pr.x + ov.w + co);
                         }
-                        *reinterpret_cast<uint4 *>(sa + (size_t)row * 128 + ((c16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const int item = pt + it * 256, row = item >> 3, c16 = item & 7;
+                            const float4 wv = s_w[tb][row];
+                            const uint32_t *a1 = reinterpret_cast<const uint32_t *>(&u[it][0]);
+                            const uint32_t *a2 = reinterpret_cast<const uint32_t *>(&u[it][1]);
+                            const uint32_t *a3 = reinterpret_cast<const uint32_t *>(&u[it][2]);
+                            const uint32_t *a4 = reinterpret_cast<const uint32_t *>(&u[it][3]);
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a1[k]));
+                                const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a2[k]));
+                                const float2 f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a3[k]));
+                                const float2 f4 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&a4[k]));
+                                const float vx = wv.x * f1.x + wv.y * f2.x + wv.z * f3.x + wv.w * f4.x;
+                                const float vy = wv.x * f1.y + wv.y * f2.y + wv.z * f3.y + wv.w * f4.y;
+                                __nv_bfloat162 b2 = __floats2bfloat162_rn(vx, vy);
+                                pk[k] = *reinterpret_cast<uint32_t *>(&b2);
+                            }
+                            *reinterpret_cast<uint4 *>(sa + (size_t)row * 128 + ((c16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy (UMMA reads smem)
+                        mbar_arrive(&full[r.stage]);
+                        r.next();
+                    } else {
+                        // split mode: every corner is read as its (hi, lo) fp16 pair, the sample is formed in fp32 exactly as
+                        // the reference does (deform_conv_cuda_kernel.cu:84-115), split again, and fills the three stages of
+                        // this channel block: hi (x w_hi), lo (x w_hi), hi (x w_lo)
+                        const __half *xh = reinterpret_cast<const __half *>(pr.x);
+                        uint32_t phi[4][4], plo[4][4];
+#pragma unroll
+                        for (int i2 = 0; i2 < 2; ++i2) {
+                            uint4 u[2][4][2];
+#pragma unroll
+                            for (int i1 = 0; i1 < 2; ++i1) {
+                                const int item = pt + (i2 * 2 + i1) * 256, row = item >> 3, c16 = item & 7;
+                                const int4 ov = s_o[tb][row];
+                                const int co = cb * kBK + c16 * 8;
+                                const int oo[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    u[i1][c][0] = *reinterpret_cast<const uint4 *>(xh + oo[c] + co);
+                                    u[i1][c][1] = *reinterpret_cast<const uint4 *>(xh + oo[c] + P.Cin + co);
+                                }
+                            }
+#pragma unroll
+                            for (int i1 = 0; i1 < 2; ++i1) {
+                                const int it = i2 * 2 + i1, item = pt + it * 256, row = item >> 3;
+                                const float4 wv = s_w[tb][row];
+                                const float wc[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    float vx = 0.f, vy = 0.f;
+#pragma unroll
+                                    for (int c = 0; c < 4; ++c) {
+                                        const uint32_t uh = reinterpret_cast<const uint32_t *>(&u[i1][c][0])[k];
+                                        const uint32_t ul = reinterpret_cast<const uint32_t *>(&u[i1][c][1])[k];
+                                        const float2 fh = __half22float2(*reinterpret_cast<const __half2 *>(&uh));
+                                        const float2 fl = __half22float2(*reinterpret_cast<const __half2 *>(&ul));
+                                        vx = fmaf(wc[c], fh.x + fl.x, vx);      // hi + lo is exact in fp32
+                                        vy = fmaf(wc[c], fh.y + fl.y, vy);
+                                    }
+                                    const __half2 h2 = __floats2half2_rn(vx, vy);
+                                    const float2 hf = __half22float2(h2);
+                                    const __half2 l2 = __floats2half2_rn(vx - hf.x, vy - hf.y);
+                                    phi[it][k] = *reinterpret_cast<const uint32_t *>(&h2);
+                                    plo[it][k] = *reinterpret_cast<const uint32_t *>(&l2);
+                                }
+                            }
+                        }
+#pragma unroll 1
+                        for (int term = 0; term < 3; ++term) {
+                            mbar_wait(&empty[r.stage], r.phase ^ 1);
+                            uint8_t *sa = smem + (size_t)r.stage * kStageBytes;
+#pragma unroll
+                            for (int it = 0; it < 4; ++it) {
+                                const int item = pt + it * 256, row = item >> 3, c16 = item & 7;
+                                const uint4 o = (term == 1) ? make_uint4(plo[it][0], plo[it][1], plo[it][2], plo[it][3])
+                                                            : make_uint4(phi[it][0], phi[it][1], phi[it][2], phi[it][3]);
+                                *reinterpret_cast<uint4 *>(sa + (size_t)row * 128 + ((c16 ^ (row & 7)) << 4)) = o;
+                            }
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            mbar_arrive(&full[r.stage]);
+                            r.next();
+                        }
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy (UMMA reads smem)
-                    mbar_arrive(&full[r.stage]);
-                    r.next();
                 }
                 tb ^= 1;
             }
@@ -960,7 +1122,7 @@ extern "C" int orp_tc_timing_collect(float *total_ms, int *launches, double *flo
 
 static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *w, int Cout, int Cout_padded, int KH,
                             int KW, int Cin, int stride, int pad, const float *bias, int relu, int out_f32,
-                            int deform, int stem, void *stream);
+                            int deform, int stem, void *stream, int split = 0, int wscale_log2 = 0);
 
 /* see include/orp_b200.h */
 extern "C" int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const void *w, int Cout, int Cout_padded, int KH,
@@ -968,6 +1130,40 @@ extern "C" int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const voi
                                int deform, void *stream)
 {
     return conv2d_bf16_impl(nprob, probs, w, Cout, Cout_padded, KH, KW, Cin, stride, pad, bias, relu, out_f32, deform, 0, stream);
+}
+
+/* see include/orp_b200.h */
+extern "C" int orp_conv2d_f16x3(int nprob, const orp_tc_problem *probs, const void *w_split, int Cout, int Cout_padded, int KH,
+                                int KW, int Cin, int stride, int pad, const float *bias, int wscale_log2, int relu,
+                                int out_f32, int deform, void *stream)
+{
+    if (wscale_log2 < 0 || wscale_log2 > 15) return fail(ORP_EINVAL, "conv2d_f16x3: weight scale exponent must be in 0..15");
+    return conv2d_bf16_impl(nprob, probs, w_split, Cout, Cout_padded, KH, KW, Cin, stride, pad, bias, relu, out_f32, deform, 0,
+                            stream, 1, wscale_log2);
+}
+
+extern "C" int orp_stem_conv_s2d_f16x3(const void *x_s2d, int N, int H, int W, const void *w_split, const float *bias,
+                                       int wscale_log2, int relu, void *out, void *stream)
+{
+    if (!x_s2d || !w_split || !out || N < 1 || H < 2 || W < 2 || (H & 1) || (W & 1))
+        return fail(ORP_EINVAL, "stem_conv_s2d_f16x3: needs even H, W");
+    if (wscale_log2 < 0 || wscale_log2 > 15) return fail(ORP_EINVAL, "stem_conv_s2d_f16x3: weight scale exponent must be in 0..15");
+    orp_tc_problem q;
+    memset(&q, 0, sizeof(q));
+    q.x = x_s2d;
+    q.N = N; q.H = H / 2 + 3; q.W = W / 2; q.out = out;
+    return conv2d_bf16_impl(1, &q, w_split, 64, 64, 4, 1, 64, 1, 0, bias, relu, 0, 0, 2, stream, 1, wscale_log2);
+}
+
+extern "C" int orp_f16x3_overflow_count(unsigned int *count, int reset)
+{
+    if (!count) return fail(ORP_EINVAL, "f16x3_overflow_count: null");
+    ORP_CUDA(cudaMemcpyFromSymbol(count, g_f16_overflow, sizeof(unsigned int)));
+    if (reset) {
+        const unsigned int z = 0;
+        ORP_CUDA(cudaMemcpyToSymbol(g_f16_overflow, &z, sizeof(z)));
+    }
+    return ORP_OK;
 }
 
 /* see include/orp_b200.h */
@@ -997,17 +1193,20 @@ extern "C" int orp_stem_conv_s2d_bf16(const void *x_s2d, int N, int H, int W, co
 
 static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *w, int Cout, int Cout_padded, int KH,
                             int KW, int Cin, int stride, int pad, const float *bias, int relu, int out_f32,
-                            int deform, int stem, void *stream)
+                            int deform, int stem, void *stream, int split, int wscale_log2)
 {
-    if (nprob < 1 || nprob > kMaxProb || !probs || !w) return fail(ORP_EINVAL, "conv2d_bf16: bad arguments");
-    if (Cin % 8) return fail(ORP_EINVAL, "conv2d_bf16: Cin must be a multiple of 8 (16-byte channel rows)");
-    if (deform && !stem && (Cin % kBK)) return fail(ORP_EINVAL, "conv2d_bf16: deformable conv needs Cin % 64 == 0");
-    if (Cout_padded % 32 || Cout_padded < Cout) return fail(ORP_EINVAL, "conv2d_bf16: padded Cout must be a multiple of 32");
+    if (nprob < 1 || nprob > kMaxProb || !probs || !w) return fail(ORP_EINVAL, "conv2d_tc: bad arguments");
+    if (Cin % 8) return fail(ORP_EINVAL, "conv2d_tc: Cin must be a multiple of 8 (16-byte channel rows)");
+    if (deform && !stem && (Cin % kBK)) return fail(ORP_EINVAL, "conv2d_tc: deformable conv needs Cin % 64 == 0");
+    if (Cout_padded % 32 || Cout_padded < Cout) return fail(ORP_EINVAL, "conv2d_tc: padded Cout must be a multiple of 32");
+    if (split && stem == 1) return fail(ORP_EINVAL, "conv2d_tc: the direct stem has no f16x3 form (use the space-to-depth stem)");
     int rc = ensure_device();
     if (rc) return rc;
     EncodeTiledFn enc = encode_fn();
-    if (!enc) return fail(ORP_ECUDA, "conv2d_bf16: cuTensorMapEncodeTiled unavailable");
+    if (!enc) return fail(ORP_ECUDA, "conv2d_tc: cuTensorMapEncodeTiled unavailable");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const CUtensorMapDataType dt16 = split ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const int T = split ? 2 : 1;             // 16-bit planes per value (hi, lo)
 
     int BN = 256;
     if (Cout_padded % 256) BN = (Cout_padded % 128 == 0) ? 128 : (Cout_padded % 64 == 0) ? 64 : 32;
@@ -1026,6 +1225,13 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     P.nprob = nprob; P.KH = KH; P.KW = KW; P.Cin = Cin; P.cin_blocks = (Cin + kBK - 1) / kBK;
     P.stride = stride; P.pad = pad;
     P.Cout = Cout; P.relu = relu; P.bias = bias; P.stem = (stem == 1) ? 1 : 0; P.s2d_stem = (stem == 2) ? 1 : 0;
+    P.split = split ? 1 : 0;
+    P.oscale = split ? ldexpf(1.f, -wscale_log2) : 1.f;
+    {
+        void *ovf = nullptr;
+        ORP_CUDA(cudaGetSymbolAddress(&ovf, g_f16_overflow));
+        P.ovf = static_cast<unsigned int *>(ovf);
+    }
     P.n_tiles_n = Cout_padded / BN;
     P.fd_ntn.set((uint32_t)P.n_tiles_n);
     int mt = 0;
@@ -1036,7 +1242,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
         pr.Ho = (q.H + 2 * pad - (KH - 1) - 1) / stride + 1;
         pr.Wo = (q.W + 2 * pad - (KW - 1) - 1) / stride + 1;
         if (stem == 1) { pr.Ho = (q.H + 6 - 7) / 2 + 1; pr.Wo = (q.W + 6 - 7) / 2 + 1; }
-        if (pr.Ho <= 0 || pr.Wo <= 0 || !q.x || !q.out) return fail(ORP_EINVAL, "conv2d_bf16: bad problem");
+        if (pr.Ho <= 0 || pr.Wo <= 0 || !q.x || !q.out) return fail(ORP_EINVAL, "conv2d_tc: bad problem");
         pr.BW = pow2_floor(pr.Wo < 128 ? pr.Wo : 128);
         if (stride * pr.BW > 256) pr.BW = 256 / stride;
         pr.BH = pow2_floor(pr.Ho < 128 / pr.BW ? pr.Ho : 128 / pr.BW);
@@ -1048,44 +1254,52 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
         pr.fd_tw.set((uint32_t)pr.tiles_w); pr.fd_th.set((uint32_t)pr.tiles_h);
         mt += pr.tiles_w * pr.tiles_h * pr.tiles_i;
         pr.out = q.out; pr.res = static_cast<const __nv_bfloat16 *>(q.residual_bf16); pr.res32 = q.residual_f32;
-        pr.x = static_cast<const __nv_bfloat16 *>(q.x); pr.offset = q.offset; pr.gn_stats = q.gn_stats;
-        if (deform && !q.offset) return fail(ORP_EINVAL, "conv2d_bf16: deformable conv needs offsets");
+        pr.x = static_cast<const __nv_bfloat16 *>(q.x); pr.offset = q.offset; pr.gn_stats = q.gn_stats; pr.mask = q.mask;
+        if (deform && !q.offset) return fail(ORP_EINVAL, "conv2d_tc: deformable conv needs offsets");
         if (!deform) {
-            cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.N};
-            cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)q.W * Cin * 2, (cuuint64_t)q.H * q.W * Cin * 2};
+            // 5-D view {channel, plane (hi / lo), w, h, image}; bf16 tensors have a single plane.  Split activations are
+            // [N,H,W,2,C]: the lo plane of a pixel follows its hi plane.
+            cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)T, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.N};
+            cuuint64_t gstr[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * 2 * T, (cuuint64_t)q.W * Cin * 2 * T,
+                                  (cuuint64_t)q.H * q.W * Cin * 2 * T};
             if (stem == 2) {
-                // space-to-depth stem: the tensor is [N, H, W + 3, 16]; a 64-element "pixel" row of the GEMM is the
-                // 4 horizontally adjacent 16-channel pixels starting at w, so consecutive w overlap (stride 32 bytes)
-                gstr[0] = 32;
-                gstr[1] = (cuuint64_t)(q.W + 3) * 32;
-                gstr[2] = (cuuint64_t)q.H * (q.W + 3) * 32;
+                // space-to-depth stem: the tensor is [T][N, H, W + 3, 16] (planes outermost); a 64-element "pixel" row of
+                // the GEMM is the 4 horizontally adjacent 16-channel pixels starting at w, so consecutive w overlap
+                // (stride 32 bytes)
+                gstr[0] = (cuuint64_t)q.N * q.H * (q.W + 3) * 32;
+                gstr[1] = 32;
+                gstr[2] = (cuuint64_t)(q.W + 3) * 32;
+                gstr[3] = (cuuint64_t)q.H * (q.W + 3) * 32;
             }
-            cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(pr.BW * stride), (cuuint32_t)(pr.BH * stride), (cuuint32_t)pr.BI};
-            cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-            CUresult r = enc(&P.tmA[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(q.x), gdim, gstr, box, estr,
+            cuuint32_t box[5] = {(cuuint32_t)kBK, 1u, (cuuint32_t)(pr.BW * stride), (cuuint32_t)(pr.BH * stride), (cuuint32_t)pr.BI};
+            cuuint32_t estr[5] = {1, 1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+            CUresult r = enc(&P.tmA[i], dt16, 5, const_cast<void *>(q.x), gdim, gstr, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_bf16: cuTensorMapEncodeTiled(A) failed");
+            if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_tc: cuTensorMapEncodeTiled(A) failed");
         }
     }
     {
-        const cuuint64_t K = (cuuint64_t)KH * KW * P.cin_blocks * kBK;   // per tap: cin_blocks x 64, zero padded
+        // weights [Cout_padded][tap][T][cin_blocks x 64] (zero padded per tap; T = 2: hi then lo)
+        const cuuint64_t K = (cuuint64_t)KH * KW * T * P.cin_blocks * kBK;
         cuuint64_t gdim[2] = {K, (cuuint64_t)Cout_padded};
         cuuint64_t gstr[1] = {K * 2};
         cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BN};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&P.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(w), gdim, gstr, box, estr,
+        CUresult r = enc(&P.tmB, dt16, 2, const_cast<void *>(w), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_bf16: cuTensorMapEncodeTiled(B) failed");
+        if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_tc: cuTensorMapEncodeTiled(B) failed");
     }
     P.num_m_tiles = mt;
     P.num_tiles = mt * P.n_tiles_n;
-    // TMA epilogue: bf16 outputs whose channel count is a multiple of 64
+    // TMA epilogue: 16-bit outputs whose channel count is a multiple of 64
     bool any_res = false;
     for (int i = 0; i < nprob; ++i) any_res = any_res || (probs[i].residual_bf16 != nullptr);
     P.tma_epi = (!out_f32 && (Cout % 64 == 0) && BN >= 64) ? 1 : 0;
-    if (getenv("ORP_TC_NO_TMA_EPI")) P.tma_epi = 0;
+    if (getenv("ORP_TC_NO_TMA_EPI") && !split) P.tma_epi = 0;
+    if (split && !out_f32 && !P.tma_epi) return fail(ORP_EINVAL, "conv2d_f16x3: 16-bit outputs need Cout % 64 == 0");
+    if (split && out_f32 && any_res) return fail(ORP_EINVAL, "conv2d_f16x3: fp32 outputs take an fp32 residual only");
     // GroupNorm statistics: fused into the TMA epilogue when every warp's 32 rows lie in one image
     bool want_gn = false, gn_ok = (P.tma_epi != 0) && Cout == 256 && !bias && !relu;
     for (int i = 0; i < nprob; ++i) {
@@ -1099,44 +1313,50 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     // epilogue-bound layers (at most 6 K blocks per tile incl. the residual's; measured: 7-15 lose a little to the
     // smaller staging/stage budget): independent epilogue warpgroups
     {
-        const int kb_total = KH * KW * P.cin_blocks + (any_res ? BN / 64 : 0);
+        const int kb_total = (KH * KW * P.cin_blocks) * (split ? 3 : 1) + (any_res ? (BN / 64) * T : 0);
         P.epi_split = (P.tma_epi && !deform && !stem && kb_total <= 6 && !getenv("ORP_TC_NO_SPLIT")) ? 1 : 0;
         if (P.epi_split) P.epi_bufs = 2;
     }
     // residual through the tensor core (TMA epilogue only; the staged epilogue adds it itself)
     P.res_mma = (P.tma_epi && any_res) ? 1 : 0;
     if (P.res_mma) {
-        if (deform) return fail(ORP_EINVAL, "conv2d_bf16: residual is not supported on the deformable path");
+        if (deform) return fail(ORP_EINVAL, "conv2d_tc: residual is not supported on the deformable path");
         for (int i = 0; i < nprob; ++i)
-            if (!probs[i].residual_bf16) return fail(ORP_EINVAL, "conv2d_bf16: residual must be given for every problem or none");
+            if (!probs[i].residual_bf16) return fail(ORP_EINVAL, "conv2d_tc: residual must be given for every problem or none");
         void *ident_ptr = nullptr;
-        ORP_CUDA(cudaGetSymbolAddress(&ident_ptr, g_ident));
+        if (split) {
+            ORP_CUDA(cudaGetSymbolAddress(&ident_ptr, g_ident16));
+            ident_ptr = static_cast<char *>(ident_ptr) + (size_t)wscale_log2 * 8192;
+        } else {
+            ORP_CUDA(cudaGetSymbolAddress(&ident_ptr, g_ident));
+        }
         cuuint64_t gdim[2] = {64, 64};
         cuuint64_t gstr[1] = {128};
         cuuint32_t box[2] = {64, 64};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&P.tmI, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ident_ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = enc(&P.tmI, dt16, 2, ident_ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_bf16: cuTensorMapEncodeTiled(identity) failed");
+        if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_tc: cuTensorMapEncodeTiled(identity) failed");
     }
     // layers whose whole weight slab for one N tile is <= 72 KiB keep it resident; stages then carry only the A tile
-    P.b_resident = (!deform && KH * KW * P.cin_blocks * BN * kBK * 2 <= 72 * 1024 && !getenv("ORP_TC_NO_BRES")) ? 1 : 0;
+    P.b_resident = (!deform && KH * KW * T * P.cin_blocks * BN * kBK * 2 <= 72 * 1024 && !getenv("ORP_TC_NO_BRES")) ? 1 : 0;
     if (P.tma_epi) {
         for (int i = 0; i < nprob; ++i) {
             const Problem &pr = P.prob[i];
-            cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)pr.Wo, (cuuint64_t)pr.Ho, (cuuint64_t)pr.N};
-            cuuint64_t gstr[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)pr.Wo * Cout * 2, (cuuint64_t)pr.Ho * pr.Wo * Cout * 2};
-            cuuint32_t box[4] = {64u, (cuuint32_t)pr.BW, (cuuint32_t)pr.BH, (cuuint32_t)pr.BI};
-            cuuint32_t estr[4] = {1, 1, 1, 1};
-            CUresult r = enc(&P.tmOut[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, pr.out, gdim, gstr, box, estr,
+            cuuint64_t gdim[5] = {(cuuint64_t)Cout, (cuuint64_t)T, (cuuint64_t)pr.Wo, (cuuint64_t)pr.Ho, (cuuint64_t)pr.N};
+            cuuint64_t gstr[4] = {(cuuint64_t)Cout * 2, (cuuint64_t)Cout * 2 * T, (cuuint64_t)pr.Wo * Cout * 2 * T,
+                                  (cuuint64_t)pr.Ho * pr.Wo * Cout * 2 * T};
+            cuuint32_t box[5] = {64u, 1u, (cuuint32_t)pr.BW, (cuuint32_t)pr.BH, (cuuint32_t)pr.BI};
+            cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+            CUresult r = enc(&P.tmOut[i], dt16, 5, pr.out, gdim, gstr, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_bf16: cuTensorMapEncodeTiled(out) failed");
+            if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_tc: cuTensorMapEncodeTiled(out) failed");
             if (pr.res) {
-                r = enc(&P.tmRes[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16 *>(pr.res), gdim, gstr, box, estr,
+                r = enc(&P.tmRes[i], dt16, 5, const_cast<__nv_bfloat16 *>(pr.res), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_bf16: cuTensorMapEncodeTiled(residual) failed");
+                if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_tc: cuTensorMapEncodeTiled(residual) failed");
             }
         }
     }
@@ -1150,7 +1370,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     if (P.b_resident && grid >= P.n_tiles_n) grid -= grid % P.n_tiles_n;       // fixed N tile per CTA
     else if (P.b_resident) P.b_resident = 0;
     const int stage_bytes = P.b_resident ? kABytes : kABytes + BN * kBK * 2;
-    const int bres_bytes = (P.b_resident ? KH * KW * P.cin_blocks * BN * kBK * 2 : 0) + (P.res_mma ? 8192 : 0);
+    const int bres_bytes = (P.b_resident ? KH * KW * T * P.cin_blocks * BN * kBK * 2 : 0) + (P.res_mma ? 8192 : 0);
     const int hc = BN < 64 ? BN : 64;
     int staging = out_f32 ? 0 : 128 * (hc * 2 + 16);
     if (P.tma_epi) staging = P.epi_bufs * 16384 * (P.epi_split ? 2 : 1);
@@ -1170,14 +1390,15 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     ORP_TC_DISPATCH(64)
     ORP_TC_DISPATCH(32)
 #undef ORP_TC_DISPATCH
-    if (!launched) return fail(ORP_EINVAL, "conv2d_bf16: unsupported tile width");
+    if (!launched) return fail(ORP_EINVAL, "conv2d_tc: unsupported tile width");
     if (lrc) return lrc;
     if (want_gn && !P.gn_fused) {
         // statistics requested but not fusable for this shape: separate pass over the bf16 output
-        if (out_f32 || Cout != 256) return fail(ORP_EINVAL, "conv2d_bf16: gn_stats needs a bf16 output with 256 channels");
+        if (out_f32 || Cout != 256) return fail(ORP_EINVAL, "conv2d_tc: gn_stats needs a 16-bit output with 256 channels");
         for (int i = 0; i < nprob; ++i)
             if (probs[i].gn_stats) {
-                int r2 = orp_gn_stats_bf16(P.prob[i].out, P.prob[i].N, P.prob[i].Ho * P.prob[i].Wo, 256, 32, probs[i].gn_stats, stream);
+                int r2 = split ? orp_gn_stats_f16x3(P.prob[i].out, P.prob[i].N, P.prob[i].Ho * P.prob[i].Wo, 256, 32, probs[i].gn_stats, stream)
+                               : orp_gn_stats_bf16(P.prob[i].out, P.prob[i].N, P.prob[i].Ho * P.prob[i].Wo, 256, 32, probs[i].gn_stats, stream);
                 if (r2) return r2;
             }
     }

@@ -8,8 +8,9 @@ Mirrors mmdet/models/detectors/orientedreppoints_detector.py:37-46:
 
 Host code is Python; every layer is a kernel of this repository called through the C ABI
 (include/orp_b200.h) on torch-owned device memory and the current torch stream.  Activations are NHWC.
-Two arithmetic engines: 'fp32' (CUDA-core FMAs - the parity arithmetic) and 'bf16' (tcgen05 tensor
-cores, fp32 accumulation in TMEM).  There is no PyTorch/cuDNN fallback for any layer.
+Three arithmetic engines: 'f16x3' (tcgen05 tensor cores on fp16 hi/lo operand pairs, three MMAs per product,
+fp32 accumulation in TMEM - fp32-faithful, the parity AND benchmark arithmetic), 'bf16' (tcgen05, single-pass bf16
+operands - 3x the rate, ~1e-2 accuracy) and 'fp32' (CUDA-core FMAs).  There is no PyTorch/cuDNN fallback for any layer.
 """
 import numpy as np
 import torch
@@ -119,6 +120,8 @@ class OrientedRepPointsDetector:
 
     def __init__(self, state_dict, depth=50, device="cuda", precision="fp32", test_cfg=None):
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:      # 'cuda' -> the current device, with its index
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.depth = depth
         self.test_cfg = dict(nms_pre=2000, min_bbox_size=0, score_thr=0.05, nms=dict(type='rnms', iou_thr=0.4),
                              max_per_img=2000)                         # configs/dota/orientedrepoints_r50_demo.py:62-67
@@ -131,8 +134,11 @@ class OrientedRepPointsDetector:
         elif precision == "bf16":
             from .engine_tc import EngineTC
             self.eng = EngineTC(self.device)
+        elif precision == "f16x3":
+            from .engine_tc import EngineTCSplit
+            self.eng = EngineTCSplit(self.device)
         else:
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+            raise ValueError("precision must be 'f16x3' (tensor cores, fp32-faithful), 'bf16' (tensor cores) or 'fp32' (CUDA cores)")
         self._load(state_dict)
         base = np.arange(-1, 2).astype(np.float64)
         off = np.stack([np.repeat(base, 3), np.tile(base, 3)], axis=1).reshape(-1)        # head :78-88 (dy,dx)
@@ -263,8 +269,12 @@ class OrientedRepPointsDetector:
         return [(c.float(), i, r.float()) for c, i, r in zip(cls, init, ref)]
 
     def forward_dense(self, img):
-        feats = self.extract_feat(img)
-        return self.head(feats), feats
+        # every launch goes to the current stream of the current device: make that this detector's device
+        with torch.cuda.device(self.device):
+            if img.device != self.device:
+                img = img.to(self.device)
+            feats = self.extract_feat(img)
+            return self.head(feats), feats
 
     # ------------------------------------------------------------------ CUDA graph of the dense graph
     def capture(self, img_shape, dtype=torch.float32):
@@ -272,6 +282,7 @@ class OrientedRepPointsDetector:
         ~180 kernel launches of a step become a single graph launch, which removes the host-side launch
         cost that otherwise dominates a one-tile step.  simple_test() replays it when the shape matches."""
         shape = tuple(img_shape)
+        torch.cuda.set_device(self.device)
         self._g_img = torch.zeros(shape, dtype=dtype, device=self.device)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
@@ -287,12 +298,17 @@ class OrientedRepPointsDetector:
         return self
 
     def forward_dense_graph(self, img):
-        self._g_img.copy_(img, non_blocking=True)
-        self._graph.replay()
+        with torch.cuda.device(self.device):
+            self._g_img.copy_(img, non_blocking=True)
+            self._graph.replay()
         return self._g_out
 
     # ------------------------------------------------------------------ simple_test
     def simple_test(self, img, img_metas=None, rescale=True, return_tensors=False):
+        with torch.cuda.device(self.device):
+            return self._simple_test(img, img_metas, rescale, return_tensors)
+
+    def _simple_test(self, img, img_metas, rescale, return_tensors):
         from .core.get_bboxes import get_bboxes
         if getattr(self, "_g_shape", None) == (tuple(img.shape), img.dtype):
             outs, _ = self.forward_dense_graph(img)

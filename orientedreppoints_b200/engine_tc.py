@@ -1,5 +1,6 @@
-"""bf16 tensor-core engine of the dense path: tcgen05 implicit-GEMM convolutions (csrc/dense_tc.cu) plus
-their memory-bound companions (csrc/dense_bf16_misc.cu).  Same interface as detector.EngineF32."""
+"""Tensor-core engines of the dense path: tcgen05 implicit-GEMM convolutions (csrc/dense_tc.cu) plus their
+memory-bound companions (csrc/dense_bf16_misc.cu, csrc/dense_f16x3_misc.cu).  EngineTC: bf16 operands (fast, ~1e-2);
+EngineTCSplit: f16x3 split operands (fp32-faithful, the parity mode).  Same interface as detector.EngineF32."""
 import ctypes
 
 import torch
@@ -111,7 +112,7 @@ class EngineTC:
         return y
 
     def _launch(self, xs, ys, tc, cout, kh, kw, cin, stride, pad, bias, relu, out_f32, deform, res=None, res32=None,
-                offsets=None, stats=None):
+                offsets=None, stats=None, masks=None):
         n = len(xs)
         arr = (_lib.TcProblem * n)()
         for i in range(n):
@@ -122,6 +123,7 @@ class EngineTC:
             arr[i].residual_f32 = res32[i].data_ptr() if res32 is not None else None
             arr[i].offset = offsets[i].data_ptr() if offsets is not None else None
             arr[i].gn_stats = stats[i].data_ptr() if stats is not None else None
+            arr[i].mask = masks[i].data_ptr() if masks is not None else None
         rc = self.lib.orp_conv2d_bf16(n, arr, _lib.ptr(tc["w"]), cout, tc["cout_p"], kh, kw, cin, stride, pad,
                                       _lib.ptr(bias), int(relu), int(out_f32), int(deform), _lib.current_stream_ptr())
         _lib.check(rc, "orp_conv2d_bf16")
@@ -191,15 +193,196 @@ class EngineTC:
                    "orp_maxpool3x3s2_bf16")
         return y
 
-    def deform_conv_multi(self, xs, offsets, L, relu=False):
+    def deform_conv_multi(self, xs, offsets, L, relu=False, masks=None):
         tc = self._tc(L)
         ys = [torch.empty((x.shape[0], x.shape[1], x.shape[2], L.cout), dtype=torch.bfloat16, device=self.device)
               for x in xs]
         self._launch(xs, ys, tc, L.cout, L.kh, L.kw, L.w_raw.shape[3], L.stride, L.pad, L.bias, relu, False, True,
-                     offsets=offsets)
+                     offsets=offsets, masks=masks)
         return ys
 
     def deform_conv(self, x, offset, L, relu=False, mask=None):
-        if mask is not None:
-            raise NotImplementedError("DCNv2 modulation is served by the fp32 engine (orp_deform_conv2d_f32)")
-        return self.deform_conv_multi([x], [offset], L, relu)[0]
+        """DCNv1; DCNv2 when mask ([N,H,W,KH*KW] fp32) is given: the modulation is folded into the bilinear corner
+        weights inside the tensor-core kernel's A-operand producers"""
+        return self.deform_conv_multi([x], [offset], L, relu, masks=None if mask is None else [mask])[0]
+
+    def to_float(self, x):
+        """activation tensor of this engine -> fp32 NHWC"""
+        return x.float()
+
+    def from_float(self, x):
+        return x.to(self.device, torch.bfloat16).contiguous()
+
+
+class EngineTCSplit(EngineTC):
+    """f16x3 arithmetic on the same tcgen05 kernels - the PARITY mode (include/orp_b200.h, "split" section): every fp32
+    value is an fp16 pair hi + lo, every product hi*hi + lo*hi + hi*lo in one fp32 TMEM accumulator.  Activations are
+    fp16 tensors [N,H,W,2,C] (hi channels, then lo channels)."""
+    name = "f16x3"
+    act_dtype = torch.float16
+
+    @staticmethod
+    def _split_weights(wp):
+        """fp32 [..] -> (hi, lo, s): fp16 halves of w * 2^s, s in 0..15 chosen so the scaled weights have rms ~ 1 (keeps
+        the lo halves in the normal fp16 range without risking overflow of the hi halves)"""
+        nz = wp[wp != 0]
+        s = 0
+        if nz.numel():
+            rms = float(nz.double().pow(2).mean().sqrt())
+            amax = float(nz.abs().max())
+            s = int(max(0, min(15, round(-float(torch.log2(torch.tensor(rms)))))))
+            while s > 0 and amax * (2.0 ** s) > 16384.0:
+                s -= 1
+        ws = wp.double() * (2.0 ** s)
+        hi = ws.to(torch.float16)
+        lo = (ws - hi.double()).to(torch.float16)
+        return hi, lo, s
+
+    def _tc(self, L):
+        if getattr(L, "tc3", None) is None:
+            w = L.w_raw                                              # [Cout, KH, KW, Cin] fp32 (unpadded Cin)
+            cout, kh, kw, cin = w.shape
+            cout_p = ((cout + 31) // 32) * 32
+            cin_p = ((cin + 63) // 64) * 64
+            wp4 = torch.zeros((cout_p, kh * kw, cin_p), dtype=torch.float32)
+            wp4[:cout, :, :cin] = w.reshape(cout, kh * kw, cin)
+            hi, lo, s = self._split_weights(wp4)
+            wp = torch.stack([hi, lo], dim=2)                        # [cout_p, taps, 2, cin_p]
+            L.tc3 = dict(w=wp.reshape(cout_p, -1).to(self.device).contiguous(), cout_p=cout_p, s=s)
+        return L.tc3
+
+    def _stem_s2d_tc(self, L):
+        if getattr(L, "tc3_s2d", None) is None:
+            w = L.w_raw                                              # [64, 7, 7, 3]
+            wp = torch.zeros((64, 4, 4, 16), dtype=torch.float32)
+            for khp in range(4):
+                for dy in range(2):
+                    ky = 2 * khp + dy - 1
+                    if not 0 <= ky <= 6:
+                        continue
+                    for kwp in range(4):
+                        for dx in range(2):
+                            kx = 2 * kwp + dx - 1
+                            if not 0 <= kx <= 6:
+                                continue
+                            ch = (dy * 2 + dx) * 3
+                            wp[:, khp, kwp, ch:ch + 3] = w[:, ky, kx, :]
+            hi, lo, s = self._split_weights(wp.reshape(64, 4, 64))   # taps = kh', 64 virtual channels = (kw', 16)
+            L.tc3_s2d = dict(w=torch.stack([hi, lo], dim=2).reshape(64, -1).to(self.device).contiguous(), s=s)
+        return L.tc3_s2d
+
+    def to_float(self, x):
+        n, h, w, _, c = x.shape
+        y = torch.empty((n, h, w, c), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.orp_split_to_f32(_lib.ptr(x), n * h * w, c, _lib.ptr(y), _lib.current_stream_ptr()), "orp_split_to_f32")
+        return y
+
+    def from_float(self, x):
+        x = x.to(self.device, torch.float32).contiguous()
+        n, h, w, c = x.shape
+        y = torch.empty((n, h, w, 2, c), dtype=torch.float16, device=self.device)
+        _lib.check(self.lib.orp_split_from_f32(_lib.ptr(x), n * h * w, c, _lib.ptr(y), _lib.current_stream_ptr()), "orp_split_from_f32")
+        return y
+
+    def overflow_count(self, reset=True):
+        c = ctypes.c_uint(0)
+        _lib.check(self.lib.orp_f16x3_overflow_count(ctypes.byref(c), int(reset)), "orp_f16x3_overflow_count")
+        return int(c.value)
+
+    def stem(self, img, L, materialise=True, mode=None):
+        n, _, h, w = img.shape
+        assert h % 2 == 0 and w % 2 == 0, "the f16x3 stem runs in space-to-depth form (even H, W)"
+        st = _lib.current_stream_ptr()
+        ws = self._stem_s2d_tc(L)
+        xs = torch.empty((2, n, h // 2 + 3, w // 2 + 3, 16), dtype=torch.float16, device=self.device)
+        _lib.check(self.lib.orp_stem_s2d_f16x3(_lib.ptr(img), n, h, w, _lib.ptr(xs), st), "orp_stem_s2d_f16x3")
+        y = torch.empty((n, h // 2, w // 2, 2, 64), dtype=torch.float16, device=self.device)
+        _lib.check(self.lib.orp_stem_conv_s2d_f16x3(_lib.ptr(xs), n, h, w, _lib.ptr(ws["w"]), _lib.ptr(L.bias), ws["s"], 1,
+                                                    _lib.ptr(y), st), "orp_stem_conv_s2d_f16x3")
+        return y
+
+    def stem_u8(self, img_u8, L, norm_cfg):
+        n, h, w, c = img_u8.shape
+        assert c == 3 and img_u8.dtype == torch.uint8 and img_u8.is_contiguous() and h % 2 == 0 and w % 2 == 0
+        st = _lib.current_stream_ptr()
+        ws = self._stem_s2d_tc(L)
+        xs = torch.empty((2, n, h // 2 + 3, w // 2 + 3, 16), dtype=torch.float16, device=self.device)
+        mean = (ctypes.c_float * 3)(*norm_cfg["mean"])
+        std = (ctypes.c_float * 3)(*norm_cfg["std"])
+        _lib.check(self.lib.orp_stem_s2d_u8_f16x3(_lib.ptr(img_u8), n, h, w, mean, std, int(bool(norm_cfg["to_rgb"])),
+                                                  _lib.ptr(xs), st), "orp_stem_s2d_u8_f16x3")
+        y = torch.empty((n, h // 2, w // 2, 2, 64), dtype=torch.float16, device=self.device)
+        _lib.check(self.lib.orp_stem_conv_s2d_f16x3(_lib.ptr(xs), n, h, w, _lib.ptr(ws["w"]), _lib.ptr(L.bias), ws["s"], 1,
+                                                    _lib.ptr(y), st), "orp_stem_conv_s2d_f16x3")
+        return y
+
+    def _launch(self, xs, ys, tc, cout, kh, kw, cin, stride, pad, bias, relu, out_f32, deform, res=None, res32=None,
+                offsets=None, stats=None, masks=None):
+        n = len(xs)
+        arr = (_lib.TcProblem * n)()
+        for i in range(n):
+            arr[i].x = xs[i].data_ptr()
+            arr[i].N, arr[i].H, arr[i].W = xs[i].shape[0], xs[i].shape[1], xs[i].shape[2]
+            arr[i].out = ys[i].data_ptr()
+            arr[i].residual_bf16 = res[i].data_ptr() if res is not None else None
+            arr[i].residual_f32 = res32[i].data_ptr() if res32 is not None else None
+            arr[i].offset = offsets[i].data_ptr() if offsets is not None else None
+            arr[i].gn_stats = stats[i].data_ptr() if stats is not None else None
+            arr[i].mask = masks[i].data_ptr() if masks is not None else None
+        rc = self.lib.orp_conv2d_f16x3(n, arr, _lib.ptr(tc["w"]), cout, tc["cout_p"], kh, kw, cin, stride, pad,
+                                       _lib.ptr(bias), tc["s"], int(relu), int(out_f32), int(deform),
+                                       _lib.current_stream_ptr())
+        _lib.check(rc, "orp_conv2d_f16x3")
+
+    def conv_multi(self, xs, L, relu=False, residual=None, out_f32=False, residual_f32=None, stats=None):
+        tc = self._tc(L)
+        ys = []
+        for x in xs:
+            n, h, w, two, cin = x.shape
+            assert two == 2 and cin == L.w_raw.shape[3] and x.dtype == torch.float16
+            ho = (h + 2 * L.pad - L.kh) // L.stride + 1
+            wo = (w + 2 * L.pad - L.kw) // L.stride + 1
+            ys.append(torch.empty((n, ho, wo, L.cout), dtype=torch.float32, device=self.device) if out_f32 else
+                      torch.empty((n, ho, wo, 2, L.cout), dtype=torch.float16, device=self.device))
+        self._launch(xs, ys, tc, L.cout, L.kh, L.kw, L.w_raw.shape[3], L.stride, L.pad, L.bias, relu, out_f32, False,
+                     res=residual, res32=residual_f32, stats=stats)
+        return ys
+
+    def gn_multi(self, xs, norm, relu=False, ups=None, stats=None):
+        st = _lib.current_stream_ptr()
+        k = len(xs)
+        if stats is None:
+            stats = []
+            for x in xs:
+                n, h, w, _, c = x.shape
+                s = torch.zeros((n, 32, 2), dtype=torch.float64, device=self.device)
+                _lib.check(self.lib.orp_gn_stats_f16x3(_lib.ptr(x), n, h * w, c, 32, _lib.ptr(s), st), "orp_gn_stats_f16x3")
+                stats.append(s)
+        ys = [torch.empty_like(x) for x in xs]
+        arr = (_lib.GnProblem * k)()
+        for i, x in enumerate(xs):
+            assert x.shape[4] == 256 and x.dtype == torch.float16
+            arr[i].x = x.data_ptr()
+            arr[i].N, arr[i].H, arr[i].W = x.shape[0], x.shape[1], x.shape[2]
+            arr[i].stats = stats[i].data_ptr()
+            arr[i].up_src = ups[i].data_ptr() if ups is not None and ups[i] is not None else None
+            arr[i].y = ys[i].data_ptr()
+        _lib.check(self.lib.orp_gn_apply_f16x3_multi(k, arr, 256, 32, _lib.ptr(norm.gamma), _lib.ptr(norm.beta), 1e-5,
+                                                     int(relu), st), "orp_gn_apply_f16x3_multi")
+        return ys
+
+    def maxpool(self, x):
+        n, h, w, _, c = x.shape
+        ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+        y = torch.empty((n, ho, wo, 2, c), dtype=torch.float16, device=self.device)
+        _lib.check(self.lib.orp_maxpool3x3s2_f16x3(_lib.ptr(x), n, h, w, c, _lib.ptr(y), _lib.current_stream_ptr()),
+                   "orp_maxpool3x3s2_f16x3")
+        return y
+
+    def deform_conv_multi(self, xs, offsets, L, relu=False, masks=None):
+        tc = self._tc(L)
+        ys = [torch.empty((x.shape[0], x.shape[1], x.shape[2], 2, L.cout), dtype=torch.float16, device=self.device)
+              for x in xs]
+        self._launch(xs, ys, tc, L.cout, L.kh, L.kw, L.w_raw.shape[3], L.stride, L.pad, L.bias, relu, False, True,
+                     offsets=offsets, masks=masks)
+        return ys

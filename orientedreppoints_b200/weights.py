@@ -28,10 +28,11 @@ def _xavier_uniform(w, gen):
     return w.uniform_(-a, a, generator=gen)
 
 
-def random_state_dict(depth=50, seed=0, reference_init=True, num_classes=16, feat=256):
+def random_state_dict(depth=50, seed=0, reference_init=True, num_classes=16, feat=256, residual_gain=1.0):
     """reference_init=True reproduces the reference's init_weights (incl. zero_init_residual and all-ones
     norm scales); False randomises norm parameters / running statistics so that every branch of the graph
-    carries signal (used by the parity tests)."""
+    carries signal (used by the parity tests); residual_gain scales the randomised scale of every block's last norm
+    (1.0 doubles the activation variance per block: fine for 16 blocks, ~1e5 after R-101's 33 - use 0.3 there)."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
 
@@ -55,7 +56,7 @@ def random_state_dict(depth=50, seed=0, reference_init=True, num_classes=16, fea
                 sd[name + ".running_mean"] = torch.zeros(c)
                 sd[name + ".running_var"] = torch.ones(c)
         else:
-            sd[name + ".weight"] = torch.empty(c).uniform_(0.5, 1.5, generator=g)
+            sd[name + ".weight"] = torch.empty(c).uniform_(0.5, 1.5, generator=g) * (residual_gain if zero_gamma else 1.0)
             sd[name + ".bias"] = torch.empty(c).normal_(0, 0.1, generator=g)
             if running:
                 sd[name + ".running_mean"] = torch.empty(c).normal_(0, 0.1, generator=g)

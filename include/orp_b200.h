@@ -82,7 +82,7 @@ void orp_reset_launch_count(void);
  * mmdet/ops/nms/src/rnms_cuda.cpp:8-17).  Ties in score: lower row index first.
  * iou_thr is a double because the fp64 reference compares against a Python float
  * (ResultMerge.py:39); COMPAT32 rounds it to fp32 like rnms_cuda's `float nms_overlap_thresh`.
- * Asynchronous; nothing is copied to the host (one exception: if the suppression-edge list
+ * Asynchronous; nothing is copied to the host (one exception: if the candidate-pair list
  * outgrows its first allocation the call synchronises once and retries with the exact size). */
 int orp_rnms(const float *dets, const int32_t *segments, int n, double iou_thr, int iou_mode,
              int union_mode, int order, int64_t *keep_out, int32_t *num_out, void *stream);
@@ -95,15 +95,17 @@ int orp_rnms(const float *dets, const int32_t *segments, int n, double iou_thr, 
 int orp_poly_nms_host(int *keep_out, int *num_out, const float *polys_host, int polys_num,
                       int polys_dim, float nms_overlap_thresh, int device_id);
 
-/* Statistics of the last orp_rnms call on this thread: candidate pairs that passed the AABB
- * sweep, pairs clipped, pairs sent to the fp64 re-evaluation, suppression edges, rounds of the
- * greedy resolution.  Requires the stream to be synchronised by the caller first. */
+/* Statistics of the last orp_rnms call on this thread.  Requires the stream to be synchronised by
+ * the caller first. */
 typedef struct {
-    int64_t pairs_total;     /* n(n-1)/2 within segments is NOT computed; this is the sweep count */
+    int64_t pairs_total;     /* pairs visited by the x-sweep (same segment, x-intervals overlap)  */
     int64_t pairs_aabb;      /* pairs whose axis-aligned hulls overlap                            */
-    int64_t pairs_clipped;   /* pairs that reached the polygon clip                              */
-    int64_t pairs_fp64;      /* pairs decided by the fp64 reference algorithm                    */
-    int64_t edges;           /* pairs with iou > thr                                             */
+    int64_t pairs_clipped;   /* pairs actually clipped: only (undecided box, KEPT candidate) pairs */
+    int64_t pairs_fp64;      /* of those, decided by the fp64 reference algorithm (error band)    */
+    int64_t edges;           /* candidate pairs: survivors of the exact-safe bounds (EXACT64), or
+                                pairs with iou > thr (COMPAT32, where every pair is evaluated)    */
+    int64_t suppressing;     /* clipped pairs with iou > thr                                      */
+    int32_t overflow;        /* 1: the candidate list outgrew its buffer in a no-sync call        */
     int32_t rounds;          /* resolution rounds                                                */
     int32_t n;
 } orp_nms_stats;

@@ -22,7 +22,8 @@ _d = ctypes.c_double
 class NmsStats(ctypes.Structure):
     _fields_ = [("pairs_total", ctypes.c_int64), ("pairs_aabb", ctypes.c_int64),
                 ("pairs_clipped", ctypes.c_int64), ("pairs_fp64", ctypes.c_int64),
-                ("edges", ctypes.c_int64), ("rounds", ctypes.c_int32), ("n", ctypes.c_int32)]
+                ("edges", ctypes.c_int64), ("suppressing", ctypes.c_int64), ("overflow", ctypes.c_int32),
+                ("rounds", ctypes.c_int32), ("n", ctypes.c_int32)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

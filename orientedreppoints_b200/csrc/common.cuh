@@ -59,7 +59,8 @@ struct Scratch {
 // nms.cu: device-resident greedy rotated NMS (see orp_rnms); flags_out = uint8 survivor flags by original index
 int run_nms(const float *dets, const int32_t *segments, int n, double thr, int iou_mode, int union_mode,
             int order, int64_t *keep_out, int32_t *num_out, cudaStream_t st, uint8_t *flags_out, bool no_sync,
-            int seg_limit /* exclusive bound on segment ids, 0 = unknown */);
+            int seg_limit /* exclusive bound on segment ids, 0 = unknown */,
+            int32_t *overflow_out /* optional device int: set to 1 when the candidate list overflowed (no_sync callers) */);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -157,11 +157,13 @@ select_keys_kernel(const uint8_t *__restrict__ keep, const uint8_t *__restrict__
 __global__ void __launch_bounds__(128)
 gather_kernel(const int32_t *__restrict__ sorted_vals, const int32_t *__restrict__ counts, const float *__restrict__ dets,
               const float *__restrict__ rp, const float *__restrict__ box, int per_img, int S, int C, int cap, int B,
-              float *__restrict__ out, int64_t *__restrict__ labels, int32_t *__restrict__ counts_out)
+              float *__restrict__ out, int64_t *__restrict__ labels, int32_t *__restrict__ counts_out,
+              const int32_t *__restrict__ nms_overflow)
 {
     const int b = blockIdx.y;
     const int n = counts[b] < cap ? counts[b] : cap;
-    if (blockIdx.x == 0 && threadIdx.x == 0) counts_out[b] = n;
+    // a candidate-list overflow inside the NMS (no host sync on this path) poisons the counts: -1 = "results invalid"
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts_out[b] = *nms_overflow ? -1 : n;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < cap; j += gridDim.x * blockDim.x) {
         float *o = out + ((size_t)b * cap + j) * 27;
         if (j < n) {
@@ -256,8 +258,11 @@ extern "C" int orp_head_postprocess(int nlevels, const float *const *cls, const 
     }
     decode_kernel<<<ceil_div((long long)B * S, 128), 128, 0, st>>>(L, v2, score_thr, scale_factor, O);
     ORP_LAUNCHED();
+    int32_t *nms_ovf = Sc.get<int32_t>(1);
+    if (!nms_ovf) return fail(ORP_ECUDA, "orp_head_postprocess: scratch allocation failed");
+    ORP_CUDA(cudaMemsetAsync(nms_ovf, 0, sizeof(int32_t), st));
     rc = run_nms(O.dets, O.segs, (int)total, iou_thr, ORP_NMS_EXACT64, ORP_UNION_NAN_KEEPS, ORP_ORDER_INDEX_ASC, nullptr,
-                 nullptr, st, keep, true, B * num_cls);
+                 nullptr, st, keep, true, B * num_cls, nms_ovf);
     if (rc) return rc;
     ORP_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * B, st));
     count_kernel<<<dim3(32, B), 256, 0, st>>>(keep, O.valid, (int)per_img, B, counts);
@@ -267,7 +272,7 @@ extern "C" int orp_head_postprocess(int nlevels, const float *const *cls, const 
     ORP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb2, sk1, sk2, sv1, sv2, (int)total, 0, sel_bits, st));
     count_launches((sel_bits + 7) / 8 + 1);
     gather_kernel<<<dim3(ceil_div(max_per_img, 128), B), 128, 0, st>>>(sv2, counts, O.dets, O.rp, O.box, (int)per_img, S,
-                                                                     num_cls, max_per_img, B, dets_out, labels_out, counts_out);
+                                                                     num_cls, max_per_img, B, dets_out, labels_out, counts_out, nms_ovf);
     ORP_LAUNCHED();
     return ORP_OK;
 }

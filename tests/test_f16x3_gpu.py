@@ -10,8 +10,9 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-4          # north_star: "within 1e-4 fp32"
 # one layer: the operand pairs carry 22 bits and the dropped lo*lo term is 2^-22, but the tensor core's fp32 accumulator
-# truncates on every K-step (measured ~6e-6 of max at K = 2304, growing with K; the bound below scales with K beyond 4096)
-OP_TOL = 2e-5
+# truncates on every K-step (error linear in the step count); with the cross terms accumulated first (dense_tc.cu KIter)
+# the measured loss is 2e-6 of max at K = 2304 and 1.8e-5 at K = 18432 - the bound below scales with K beyond 4096
+OP_TOL = 8e-6
 
 
 def _nchw(x):
@@ -108,8 +109,10 @@ def test_deform_conv_f16x3_vs_fp64(cuda, eng):
             masks.append(None if m is None else m.permute(0, 2, 3, 1).contiguous().to(cuda))
         ys = eng.deform_conv_multi(xs, offs, L, masks=masks if use_mask else None)
         for y, ref in zip(ys, refs):
-            # bilinear weights and the sample are formed in fp32 as in the reference kernel: ~1e-6
-            assert _rel(_nchw(eng.to_float(y)).cpu(), ref) < OP_TOL, use_mask
+            # bilinear weights and the sample are formed in fp32 as in the reference kernel; the deformable K walk is
+            # (tap, block, term) - the sampled tile is built once for its three terms - so the accumulator loss is that of
+            # 3K/16 steps (measured 1.0e-5 at K = 2304)
+            assert _rel(_nchw(eng.to_float(y)).cpu(), ref) < 2.5e-5, use_mask
 
 
 def test_deform_conv_bf16_mask(cuda):

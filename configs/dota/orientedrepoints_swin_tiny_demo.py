@@ -1,0 +1,18 @@
+# Model / test settings of the reference's configs/dota/orientedrepoints_swin_tiny_demo.py:1-75 (inference-relevant part).
+norm_cfg = dict(type='GN', num_groups=32, requires_grad=True)
+_losses = dict(
+    loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+    loss_rbox_init=dict(type='GIoULoss', loss_weight=0.375), loss_rbox_refine=dict(type='GIoULoss', loss_weight=1.0),
+    loss_spatial_init=dict(type='SpatialBorderLoss', loss_weight=0.05),
+    loss_spatial_refine=dict(type='SpatialBorderLoss', loss_weight=0.1))
+model = dict(
+    type='OrientedRepPointsDetector', pretrained=None,
+    backbone=dict(type='SwinTransformer', embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7,
+                  mlp_ratio=4., qkv_bias=True, qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.2, ape=False,
+                  patch_norm=True, out_indices=(1, 2, 3), use_checkpoint=False),
+    neck=dict(type='FPN', in_channels=[192, 384, 768], out_channels=256, num_outs=5, norm_cfg=norm_cfg),
+    bbox_head=dict(type='OrientedRepPointsHead', num_classes=16, in_channels=256, feat_channels=256, point_feat_channels=256,
+                   stacked_convs=3, num_points=9, gradient_mul=0.3, point_strides=[8, 16, 32, 64, 128], point_base_scale=2,
+                   norm_cfg=norm_cfg, top_ratio=0.4, **_losses))
+test_cfg = dict(nms_pre=2000, min_bbox_size=0, score_thr=0.05, nms=dict(type='rnms', iou_thr=0.4), max_per_img=2000)
+img_norm_cfg = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_rgb=True)

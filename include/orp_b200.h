@@ -289,6 +289,10 @@ int orp_gn_stats_f16x3(const void *x, int N, int HW, int C, int groups, double *
 /* fp32 NHWC [N,H,W,C] <-> split fp16 [N,H,W,2,C] (boundary conversions: DeformConv operator surface, tests) */
 int orp_split_from_f32(const float *x, long long pixels, int C, void *y_split, void *stream);
 int orp_split_to_f32(const void *x_split, long long pixels, int C, float *y, void *stream);
+/* per image: row-major [R, Cc] fp32 -> its transpose [Cc, R] (NCHW <-> NHWC with R = C, Cc = H*W or the reverse) */
+int orp_transpose_f32(const float *x, int N, int R, int Cc, float *y, void *stream);
+/* NCHW fp32 [N, C, HW] -> split fp16 NHWC [N, HW, 2, C] in one pass (C % 8 == 0) */
+int orp_nchw_f32_to_split(const float *x, int N, int C, int HW, void *y_split, void *stream);
 
 /* conv1 of the ResNet stem (7x7, stride 2, pad 3, 3 channels; resnet.py:495) + folded BN + ReLU straight
  * from the NCHW fp32 image: the im2col rows (k = (kh*7+kw)*3 + c, K padded 147 -> 192) are built in shared

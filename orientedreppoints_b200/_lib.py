@@ -73,6 +73,8 @@ SIGNATURES = {
     "orp_gn_apply_f16x3_multi": (_i, [_i, _vp, _i, _i, _vp, _vp, _f, _i, _vp]),
     "orp_split_from_f32": (_i, [_vp, ctypes.c_longlong, _i, _vp, _vp]),
     "orp_split_to_f32": (_i, [_vp, ctypes.c_longlong, _i, _vp, _vp]),
+    "orp_transpose_f32": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "orp_nchw_f32_to_split": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "orp_layernorm_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _i, _vp, _vp]),
     "orp_window_attention_bf16": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _vp, _vp]),
     "orp_patch_embed_rows_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp]),

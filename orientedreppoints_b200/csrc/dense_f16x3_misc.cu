@@ -283,6 +283,43 @@ stem_s2d_split_kernel(const void *__restrict__ img_v, int N, int H, int W, float
     }
 }
 
+
+// ---- layout conversions at the operator boundary (the reference's ops take NCHW fp32, mmdet/ops/dcn/deform_conv.py:17-58)
+// per image a [R, Cc] row-major matrix -> its transpose [Cc, R]; 32 x 32 tiles through shared memory, both sides coalesced
+// MODE 0: fp32 -> fp32.  MODE 1: fp32 [C, HW] -> split fp16 [HW, 2, C] (rows = channels, columns = pixels)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float *__restrict__ x, int R, int Cc, void *__restrict__ yv)
+{
+    __shared__ float t[32][33];
+    const int n = blockIdx.z;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;             // 32 x 8
+    const float *xi = x + (size_t)n * R * Cc;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = r0 + ty + k * 8, c = c0 + tx;
+        t[ty + k * 8][tx] = (r < R && c < Cc) ? xi[(size_t)r * Cc + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + k * 8, r = r0 + tx;                      // output row = input column
+        if (c < Cc && r < R) {
+            const float v = t[tx][ty + k * 8];
+            if (MODE == 0) {
+                static_cast<float *>(yv)[(size_t)n * R * Cc + (size_t)c * R + r] = v;
+            } else {
+                const float a = fminf(fmaxf(v, -65504.f), 65504.f);
+                const __half h = __float2half_rn(a);
+                __half *y = static_cast<__half *>(yv) + ((size_t)n * Cc + c) * 2 * R;   // pixel c: [2][R channels]
+                y[r] = h;
+                y[R + r] = __float2half_rn(a - __half2float(h));
+            }
+        }
+    }
+}
+
 }  // namespace
 }  // namespace orp
 
@@ -399,6 +436,29 @@ extern "C" int orp_gn_apply_f16x3_multi(int nprob, const orp_gn_problem *probs, 
     if (imgs > 65535) return fail(ORP_EINVAL, "gn_apply_f16x3: too many images");
     dim3 grid((unsigned)((max_items + 1023) / 1024), (unsigned)imgs);
     gn_apply_split_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(P);
+    ORP_LAUNCHED();
+    return ORP_OK;
+}
+
+extern "C" int orp_transpose_f32(const float *x, int N, int R, int Cc, float *y, void *stream)
+{
+    if (!x || !y || N < 1 || R < 1 || Cc < 1 || N > 65535) return fail(ORP_EINVAL, "transpose_f32: bad arguments");
+    int rc = ensure_device();
+    if (rc) return rc;
+    dim3 grid((unsigned)ceil_div(Cc, 32), (unsigned)ceil_div(R, 32), (unsigned)N);
+    if (grid.y > 65535) return fail(ORP_EINVAL, "transpose_f32: too many rows");
+    transpose_kernel<0><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, R, Cc, y);
+    ORP_LAUNCHED();
+    return ORP_OK;
+}
+
+extern "C" int orp_nchw_f32_to_split(const float *x, int N, int C, int HW, void *y_split, void *stream)
+{
+    if (!x || !y_split || N < 1 || C < 8 || (C % 8) || HW < 1 || N > 65535) return fail(ORP_EINVAL, "nchw_f32_to_split: C must be a multiple of 8");
+    int rc = ensure_device();
+    if (rc) return rc;
+    dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)ceil_div(C, 32), (unsigned)N);
+    transpose_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, C, HW, y_split);
     ORP_LAUNCHED();
     return ORP_OK;
 }

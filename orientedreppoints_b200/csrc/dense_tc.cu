@@ -86,6 +86,7 @@ struct alignas(64) TcParams {
     CUtensorMap tmI;                          // 64 x 64 bf16 identity (residual add on the tensor core)
     Problem prob[kMaxProb];
     int tma_epi, epi_bufs;                    // TMA epilogue on/off; output staging buffers (1 or 2)
+    int epi_merge;                            // split mode, memory-bound layers: hi and lo tiles of a 64-column group leave in ONE pass
     int b_resident;                           // short-K layers: the whole weight slab of this CTA's N tile stays in shared memory
     int res_mma;                              // residual added by the tensor core: extra K blocks  R[128x64] * I[64x64]
     int epi_split;                            // epilogue-bound layers: the two epilogue warpgroups work on alternate tiles (one per accumulator buffer)
@@ -547,11 +548,14 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 // tile and leave with cp.async.bulk.tensor (coalescing and partial-tile clipping by hardware).  A
                 // residual is already in the accumulator (added by the tensor core, see the MMA warp).
                 // With eight epilogue warps each warp owns one 32-column half of the pass.
-                const uint32_t obuf_u = smem_u32(stage_out) + (uint32_t)(grp * P.epi_bufs) * 16384u;   // [epi_bufs][16 KiB] per group
+                const uint32_t slot = P.epi_merge ? 32768u : 16384u;     // a staging slot: one 16 KiB tile (hi | lo when merged)
+                const uint32_t obuf_u = smem_u32(stage_out) + (uint32_t)(grp * P.epi_bufs) * slot;   // [epi_bufs][slot] per group
                 const uint32_t bias_u = smem_u32(s_bias);
                 const bool io = (et == 0);
                 constexpr int kPasses = BN / 64;
-                const int oterms = P.split ? 2 : 1;                      // split mode: a hi pass and a lo pass per 64 columns
+                // split mode: a hi pass and a lo pass per 64 columns (compute-bound layers: one 16 KiB staging tile), or both
+                // halves in one pass (memory-bound layers: half the TMEM reads, barriers and fp32 work per output value)
+                const int oterms = (P.split && !P.epi_merge) ? 2 : 1;
                 if (nt != bias_nt) {                                     // bias slice changes only with the N tile
                     bar_sync(bar_a, nthr);                               // previous tile's bias reads are done
                     for (int c = et; c < BN; c += nthr) s_bias[c] = (P.bias && nt * BN + c < P.Cout) ? P.bias[nt * BN + c] : 0.f;
@@ -560,7 +564,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 float amax = 0.f;
 #pragma unroll 1
                 for (int pass = 0; pass < kPasses * oterms; ++pass) {
-                    const int half = P.split ? (pass >> 1) : pass, oterm = P.split ? (pass & 1) : 0;
+                    const int half = oterms == 2 ? (pass >> 1) : pass, oterm = oterms == 2 ? (pass & 1) : 0;
                     if (io) {
                         if (P.epi_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -571,7 +575,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                         tcgen05_fence_after();
                     }
                     float gn_s = 0.f, gn_q = 0.f;
-                    const uint32_t orow = obuf_u + (uint32_t)ob * 16384u + (uint32_t)rrow * 128u;
+                    const uint32_t orow = obuf_u + (uint32_t)ob * slot + (uint32_t)rrow * 128u;
 #pragma unroll 1
                     for (int ch = ch0; ch < 2; ch += chs) {
                         uint32_t v[32];
@@ -603,23 +607,26 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             }
                             uint32_t pk[4];
                             if (P.split) {
-                                // x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significand bits
+                                // x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significand bits.  Values beyond the fp16
+                                // range become inf / nan in the output AND are counted (P.ovf): never silent.
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
                                     if (P.relu == 1) f[j] = fmaxf(f[j], 0.f);
-                                    amax = fmaxf(amax, fabsf(f[j]));
-                                    f[j] = fminf(fmaxf(f[j], -65504.f), 65504.f);
+                                    if (oterm == 0) amax = fmaxf(amax, fabsf(f[j]));
                                 }
+                                uint32_t pl[4];
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
                                     const __half2 h2 = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
-                                    __half2 o2 = h2;
-                                    if (oterm) {
+                                    pk[k] = *reinterpret_cast<const uint32_t *>(&h2);
+                                    if (P.epi_merge || oterm) {
                                         const float2 hf = __half22float2(h2);
-                                        o2 = __floats2half2_rn(f[2 * k] - hf.x, f[2 * k + 1] - hf.y);
+                                        const __half2 l2 = __floats2half2_rn(f[2 * k] - hf.x, f[2 * k + 1] - hf.y);
+                                        pl[k] = *reinterpret_cast<const uint32_t *>(&l2);
                                     }
-                                    pk[k] = *reinterpret_cast<const uint32_t *>(&o2);
                                 }
+                                if (P.epi_merge) sts128(orow + 16384u + sw, make_uint4(pl[0], pl[1], pl[2], pl[3]));
+                                else if (oterm) { pk[0] = pl[0]; pk[1] = pl[1]; pk[2] = pl[2]; pk[3] = pl[3]; }
                             } else {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
@@ -660,8 +667,13 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                     if (io) {
                         asm volatile(
                             "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-                            ::"l"(&P.tmOut[pi]), "r"(obuf_u + (uint32_t)ob * 16384u), "r"(nt * BN + half * 64), "r"(oterm),
+                            ::"l"(&P.tmOut[pi]), "r"(obuf_u + (uint32_t)ob * slot), "r"(nt * BN + half * 64), "r"(oterm),
                               "r"(wb * pr.BW), "r"(hb * pr.BH), "r"(ib * pr.BI) : "memory");
+                        if (P.epi_merge)
+                            asm volatile(
+                                "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                                ::"l"(&P.tmOut[pi]), "r"(obuf_u + (uint32_t)ob * slot + 16384u), "r"(nt * BN + half * 64), "r"(1),
+                                  "r"(wb * pr.BW), "r"(hb * pr.BH), "r"(ib * pr.BI) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     if (++ob == P.epi_bufs) ob = 0;
@@ -1245,6 +1257,9 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
         if (pr.Ho <= 0 || pr.Wo <= 0 || !q.x || !q.out) return fail(ORP_EINVAL, "conv2d_tc: bad problem");
         pr.BW = pow2_floor(pr.Wo < 128 ? pr.Wo : 128);
         if (stride * pr.BW > 256) pr.BW = 256 / stride;
+        // (measured: 16 x 8 pixel tiles for the deformable variant change nothing - 1361 vs 1334 us per f16x3 launch, and neither
+        // does the spread of the offsets: the gather runs at the ~47 GB/s per SM L2 -> SM ceiling whatever its locality)
+        if (deform && !stem && pr.BW > 16 && getenv("ORP_TC_DCN_2DTILES")) pr.BW = 16;
         pr.BH = pow2_floor(pr.Ho < 128 / pr.BW ? pr.Ho : 128 / pr.BW);
         pr.BI = 128 / (pr.BW * pr.BH);
         pr.lbw = 0; while ((1 << pr.lbw) < pr.BW) ++pr.lbw;
@@ -1310,6 +1325,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     const bool mem_bound = any_res || (KH * KW * (Cin / kBK) <= 8);
     P.epi_bufs = mem_bound ? 2 : 1;          // a second staging tile costs compute-bound layers a main-loop stage
     if (const char *e = getenv("ORP_TC_EPI_BUFS")) P.epi_bufs = atoi(e) == 1 ? 1 : 2;
+    P.epi_merge = (split && P.tma_epi && (mem_bound || stem == 2) && !getenv("ORP_TC_NO_MERGE")) ? 1 : 0;
     // epilogue-bound layers (at most 6 K blocks per tile incl. the residual's; measured: 7-15 lose a little to the
     // smaller staging/stage budget): independent epilogue warpgroups
     {
@@ -1373,7 +1389,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     const int bres_bytes = (P.b_resident ? KH * KW * T * P.cin_blocks * BN * kBK * 2 : 0) + (P.res_mma ? 8192 : 0);
     const int hc = BN < 64 ? BN : 64;
     int staging = out_f32 ? 0 : 128 * (hc * 2 + 16);
-    if (P.tma_epi) staging = P.epi_bufs * 16384 * (P.epi_split ? 2 : 1);
+    if (P.tma_epi) staging = P.epi_bufs * (P.epi_merge ? 32768 : 16384) * (P.epi_split ? 2 : 1);
     int stages = (int)((227 * 1024 - 4096 - 1024 - staging - bres_bytes) / stage_bytes);
     if (stages > kStagesMax) stages = kStagesMax;
     if (deform && stages > 3) stages = 3;     // leave L1 capacity for the bilinear gather (corner reuse between neighbouring pixels)

@@ -72,7 +72,7 @@ nms_prep_kernel(const float *__restrict__ dets, const int32_t *__restrict__ segm
     uint32_t seg = segments ? (uint32_t)segments[i] : 0u;
     // non-finite boxes go to the very end of the sweep order and never take part in it
     uint64_t key = finite ? (((uint64_t)(seg & 0x7FFFFFFFu) << 32) | orderable(xmin)) : ~0ull;
-    sweep_key[i] = key;
+    if (sweep_key) sweep_key[i] = key;                     // COMPAT32 bookkeeping only; EXACT64 registers boxes separately
     iota[i] = i;
 }
 
@@ -81,6 +81,127 @@ nms_rank_kernel(const int32_t *__restrict__ order, int n, int32_t *__restrict__ 
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < n) rank[order[r]] = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// EXACT64 candidate search: per-box arrays (by ORIGINAL index) + "registrations" for the sweep
+// ---------------------------------------------------------------------------------------------
+// Global facts the registration needs, gathered without a host round trip.
+struct NmsGlobal {
+    unsigned int ymin_key;        // orderable(min AABB ymin) over finite boxes
+    unsigned int maxh_bits;       // float bits of the largest AABB height (non-negative: bit order == value order)
+    double sumh;                  // sum of AABB heights
+    unsigned int count;           // finite boxes
+};
+
+__device__ __forceinline__ float from_orderable(uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+// per box: vertices, AABB, area sign (convexity); block-reduced global statistics
+__global__ void __launch_bounds__(256)
+nms_boxes_kernel(const float *__restrict__ dets, int n, float4 *__restrict__ baabb, float4 *__restrict__ v01,
+                 float4 *__restrict__ v23, float *__restrict__ area, NmsGlobal *__restrict__ G)
+{
+    __shared__ unsigned int s_ymin, s_maxh, s_cnt;
+    __shared__ float s_sum;
+    if (threadIdx.x == 0) { s_ymin = 0xFFFFFFFFu; s_maxh = 0u; s_cnt = 0u; s_sum = 0.f; }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float *d = dets + (size_t)i * 9;
+        float c[8];
+        bool finite = true;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { c[k] = d[k]; finite = finite && isfinite(c[k]); }
+        const float xmin = fminf(fminf(c[0], c[2]), fminf(c[4], c[6])), xmax = fmaxf(fmaxf(c[0], c[2]), fmaxf(c[4], c[6]));
+        const float ymin = fminf(fminf(c[1], c[3]), fminf(c[5], c[7])), ymax = fmaxf(fmaxf(c[1], c[3]), fmaxf(c[5], c[7]));
+        baabb[i] = make_float4(xmin, ymin, xmax, ymax);
+        v01[i] = make_float4(c[0], c[1], c[2], c[3]);
+        v23[i] = make_float4(c[4], c[5], c[6], c[7]);
+        // area about the box's own first vertex (small coordinates -> accurate); negative marks "not a convex
+        // quadrilateral": such boxes are never pruned by the area bound and are always decided by the fp64 reference
+        // algorithm (which accepts arbitrary quadrilaterals); NaN area (non-finite box) never takes part
+        const float ux = c[2] - c[0], uy = c[3] - c[1], vx = c[4] - c[0], vy = c[5] - c[1], wx = c[6] - c[0], wy = c[7] - c[1];
+        area[i] = quad_is_convex(c) ? 0.5f * fabsf((ux * vy - uy * vx) + (vx * wy - vy * wx)) : -1.0f;
+        if (finite) {
+            atomicMin(&s_ymin, orderable(ymin));
+            atomicMax(&s_maxh, __float_as_uint(ymax - ymin));
+            atomicAdd(&s_sum, ymax - ymin);
+            atomicAdd(&s_cnt, 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) {
+        atomicMin(&G->ymin_key, s_ymin);
+        atomicMax(&G->maxh_bits, s_maxh);
+        atomicAdd(&G->sumh, (double)s_sum);
+        atomicAdd(&G->count, s_cnt);
+    }
+}
+
+// Strip geometry shared by registration and sweep (identical arithmetic on both sides): strips of height s along y,
+// s >= max AABB height / 3 so that a box overlaps at most 4 strips; R == 1 disables the strips (one strip holds everything).
+struct Strips {
+    float y0, s;
+    __device__ __forceinline__ int of(float y) const { return (int)floorf((y - y0) / s); }
+};
+__device__ __forceinline__ Strips make_strips(const NmsGlobal *G, int R)
+{
+    Strips S;
+    S.y0 = from_orderable(G->ymin_key);
+    if (R == 1 || G->count == 0) { S.s = 3.0e38f; return S; }
+    const float maxh = __uint_as_float(G->maxh_bits), meanh = (float)(G->sumh / (double)G->count);
+    S.s = fmaxf(fmaxf(1.5f * meanh, maxh * (1.0001f / 3.0f)), 1e-6f);
+    return S;
+}
+
+// R registration slots per box: one per strip its AABB overlaps (key = segment : strip : xmin), the rest padded with
+// all-ones keys that sort to the end.  A pair is examined only in the strip that holds max(ymin_i, ymin_j), so it is
+// seen exactly once although both boxes may be registered in several common strips.
+__global__ void __launch_bounds__(256)
+nms_regs_kernel(const float4 *__restrict__ baabb, const int32_t *__restrict__ segments, int n, int R,
+                const NmsGlobal *__restrict__ G, uint64_t *__restrict__ keys, int32_t *__restrict__ vals)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 b = baabb[i];
+    const bool finite = isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w);
+    const Strips S = make_strips(G, R);
+    int t0 = 0, t1 = -1;
+    if (finite) { t0 = S.of(b.y); t1 = S.of(b.w); if (R == 1) t1 = t0 = 0; if (t1 - t0 > R - 1) t1 = t0 + R - 1; }
+    if (R == 1) {
+        // no strips: the whole upper word is the segment id (31 bits)
+        const uint64_t seg = segments ? (uint64_t)((uint32_t)segments[i] & 0x7FFFFFFFu) : 0ull;
+        keys[i] = finite ? ((seg << 32) | orderable(b.x)) : ~0ull;
+        vals[i] = i;
+        return;
+    }
+    const uint64_t seg = segments ? (uint64_t)((uint32_t)segments[i] & 0x7FFFu) : 0ull;
+    for (int k = 0; k < R; ++k) {
+        const int t = t0 + k;
+        keys[(size_t)i * R + k] = (t <= t1) ? ((seg << 48) | ((uint64_t)(uint32_t)(t & 0xFFFF) << 32) | orderable(b.x)) : ~0ull;
+        vals[(size_t)i * R + k] = i;
+    }
+}
+
+// sorted registrations -> the arrays the sweep streams: AABB, (segment : strip) group, box id
+__global__ void __launch_bounds__(256)
+nms_slots_kernel(const uint64_t *__restrict__ keys, const int32_t *__restrict__ vals, const float4 *__restrict__ baabb, int m,
+                 float4 *__restrict__ aabb_s, int32_t *__restrict__ grp_s, int32_t *__restrict__ bid_s, int32_t *__restrict__ nvalid)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m) return;
+    const uint64_t k = keys[s];
+    const bool valid = (k != ~0ull);
+    const int i = vals[s];
+    aabb_s[s] = baabb[i];
+    grp_s[s] = (int32_t)(k >> 32);
+    bid_s[s] = i;
+    const bool prev_valid = (s == 0) ? true : (keys[s - 1] != ~0ull);
+    if (!valid && prev_valid) *nvalid = s;                   // first padding slot = number of registrations
+    if (valid && s == m - 1) *nvalid = m;
 }
 
 // gather boxes into structure-of-arrays in `perm` order
@@ -168,10 +289,14 @@ __device__ __forceinline__ bool decide_exact(const Quad &A, const Quad &B, const
 }
 
 struct SweepParams {
-    const float4 *aabb, *v01, *v23;
-    const int32_t *rk, *sg;
+    const float4 *aabb_s;                      // per registration slot (sweep order)
+    const int32_t *grp_s, *bid_s;
+    const float4 *v01, *v23;                   // per box (original index)
     const float *area;
+    const int32_t *rank;
     const int32_t *nvalid;
+    const NmsGlobal *G;
+    int R;
     int2 *edges;
     int32_t *indeg;
     unsigned long long edge_cap;
@@ -210,10 +335,14 @@ __device__ __forceinline__ bool frame_prune(const float *p, const float *q, floa
     return (ou * ov) < 0.998f * kthr_sum * l2;                   // inter <= ou*ov/l2 < thr/(1+thr) * (A+B)
 }
 
+// One warp per registration slot i: walk the slots after it while they stay in the same (segment, strip) group and
+// start left of i's right edge; lanes test AABBs (coalesced float4 reads of the sorted array), survivors of the area bound
+// are compacted into a per-warp shared-memory queue, filtered by the projection bounds in both boxes' frames, and emitted
+// as candidate pairs (worse-ranked box, better-ranked box) by ORIGINAL index.
 __global__ void __launch_bounds__(kSweepWarps * 32, 6)
 nms_sweep_kernel(SweepParams P)
 {
-    __shared__ int32_t q1[kSweepWarps][64];    // AABB + area-bound survivors
+    __shared__ int32_t q1[kSweepWarps][64];    // (registration slot) AABB + area-bound survivors
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nv = *P.nvalid;
     const int nwarps = gridDim.x * kSweepWarps;
@@ -221,38 +350,42 @@ nms_sweep_kernel(SweepParams P)
     const float thrf = (float)P.thr;
     const float kthr = thrf / (1.f + thrf);
     const unsigned lt = (1u << lane) - 1u;
+    const Strips S = make_strips(P.G, P.R);
 
     for (int i = blockIdx.x * kSweepWarps + wib; i < nv; i += nwarps) {
-        const float4 ba = P.aabb[i];
-        const int seg_i = P.sg[i];
-        const int rk_i = P.rk[i];
-        const float area_i = P.area[i];
-        Quad A;
+        const float4 ba = P.aabb_s[i];
+        const int grp_i = P.grp_s[i];
+        const int strip_i = grp_i & 0xFFFF;
+        const int bi = P.bid_s[i];
+        const int rk_i = P.rank[bi];
+        const float area_i = P.area[bi];
+        float A[8];
         {
-            float4 t0 = P.v01[i], t1 = P.v23[i];
-            A.c[0] = t0.x; A.c[1] = t0.y; A.c[2] = t0.z; A.c[3] = t0.w;
-            A.c[4] = t1.x; A.c[5] = t1.y; A.c[6] = t1.z; A.c[7] = t1.w;
+            const float4 t0 = P.v01[bi], t1 = P.v23[bi];
+            A[0] = t0.x; A[1] = t0.y; A[2] = t0.z; A[3] = t0.w; A[4] = t1.x; A[5] = t1.y; A[6] = t1.z; A[7] = t1.w;
         }
         int n1 = 0;
         bool more = true;
         for (int base = i + 1;; base += 32) {
-            // ---- stage 0: walk the x-interval, AABB test + area bound -> q1
+            // ---- stage 0: walk the x-interval, AABB test + strip ownership + area bound -> q1
             bool hit = false;
             const int j = base + lane;
             if (more) {
                 bool cont = false;
                 if (j < nv) {
-                    const float4 bb = P.aabb[j];
-                    cont = (P.sg[j] == seg_i) && (bb.x <= ba.z);
+                    const float4 bb = P.aabb_s[j];
+                    cont = (P.grp_s[j] == grp_i) && (bb.x <= ba.z);
                     if (cont) {
                         ++c_swept;
                         hit = (bb.x < ba.z) && (bb.y < ba.w) && (bb.w > ba.y);
+                        // the pair belongs to the strip holding the top of the AABB intersection
+                        if (hit && P.R > 1) hit = ((S.of(fmaxf(ba.y, bb.y)) & 0xFFFF) == strip_i);
                         if (hit) {
                             ++c_aabb;
                             // exact-safe area bound: inter <= min(area_i, area_j, |AABB_i ^ AABB_j|)
                             const float iw = fminf(ba.z, bb.z) - fmaxf(ba.x, bb.x);
                             const float ih = fminf(ba.w, bb.w) - fmaxf(ba.y, bb.y);
-                            const float area_j = P.area[j];
+                            const float area_j = P.area[P.bid_s[j]];
                             const float imax = fminf(fminf(area_i, area_j), iw * ih);
                             if (imax * (1.f + thrf) < 0.999f * thrf * (area_i + area_j) && imax > 0.f) hit = false;
                         }
@@ -261,28 +394,27 @@ nms_sweep_kernel(SweepParams P)
                 more = __all_sync(0xffffffffu, cont);
             }
             const unsigned hm = __ballot_sync(0xffffffffu, hit);
-            if (hit) q1[wib][n1 + __popc(hm & lt)] = j;
+            if (hit) q1[wib][n1 + __popc(hm & lt)] = P.bid_s[j];
             n1 += __popc(hm);
             __syncwarp();
-            // ---- stage 1: projection bounds in both frames
+            // ---- stage 1: projection bounds in both frames -> candidate pairs
             while (n1 >= 32 || (!more && n1 > 0)) {
                 const int take = n1 < 32 ? n1 : 32;
                 bool pass = false;
-                int jj = 0;
+                int bj = 0;
                 if (lane < take) {
-                    jj = q1[wib][n1 - take + lane];
-                    const float area_j = P.area[jj];
+                    bj = q1[wib][n1 - take + lane];
+                    const float area_j = P.area[bj];
                     pass = true;
                     if (area_i >= 0.f && area_j >= 0.f) {             // both convex: bounds are valid
                         float b[8];
-                        const float4 t0 = P.v01[jj], t1 = P.v23[jj];
+                        const float4 t0 = P.v01[bj], t1 = P.v23[bj];
                         b[0] = t0.x; b[1] = t0.y; b[2] = t0.z; b[3] = t0.w; b[4] = t1.x; b[5] = t1.y; b[6] = t1.z; b[7] = t1.w;
                         const float ks = kthr * (area_i + area_j);
-                        if (ks > 0.f && (frame_prune(A.c, b, ks) || frame_prune(b, A.c, ks))) pass = false;
+                        if (ks > 0.f && (frame_prune(A, b, ks) || frame_prune(b, A, ks))) pass = false;
                     }
                 }
                 n1 -= take;
-                // ---- candidates: (worse-ranked slot, better-ranked slot), appended warp-aggregated
                 const unsigned pm = __ballot_sync(0xffffffffu, pass);
                 if (pm) {
                     unsigned long long basep = 0;
@@ -290,8 +422,8 @@ nms_sweep_kernel(SweepParams P)
                     basep = __shfl_sync(0xffffffffu, basep, 0);
                     if (pass) {
                         const unsigned long long pos = basep + __popc(pm & lt);
-                        const bool i_worse = rk_i > P.rk[jj];
-                        const int lo = i_worse ? i : jj, hi = i_worse ? jj : i;
+                        const bool i_worse = rk_i > P.rank[bj];
+                        const int lo = i_worse ? bi : bj, hi = i_worse ? bj : bi;
                         if (pos < P.edge_cap) {
                             P.edges[pos] = make_int2(lo, hi);
                             atomicAdd(&P.indeg[lo], 1);
@@ -451,8 +583,9 @@ nms_resolve_kernel(const int32_t *__restrict__ offs, const int32_t *__restrict__
 
 // Lazy variant (EXACT64 mode): adj holds CANDIDATE pairs by sweep slot; a candidate is clipped only when its better-ranked
 // box is known to be kept and the worse one is still undecided.  Per round:
-//   phase A (warp per undecided box): scan the candidate list; kept candidates not evaluated yet go to a global work
-//            queue; a box with nothing queued and no undecided candidate left is kept.
+//   phase A (warp per undecided box): scan the candidate list, dropping entries that can no longer matter (suppressed
+//            candidates, pairs already proven harmless) so that later rounds only touch live entries; kept candidates not
+//            evaluated yet go to a global work queue; a box with nothing queued and no undecided candidate left is kept.
 //   phase B (thread per queue entry): decide the pair exactly; "suppresses" -> the box is suppressed, otherwise the
 //            candidate is struck from the list (adj = -1).
 // Statuses only move undecided -> final and a box is decided from final statuses only, so the fixed point is the greedy
@@ -461,7 +594,8 @@ struct LazyParams {
     const int32_t *offs;
     int32_t *adj;
     int n;
-    volatile uint8_t *status;                  // by sweep slot: 0 undecided, 1 kept, 2 suppressed
+    volatile uint8_t *status;                  // by original index: 0 undecided, 1 kept, 2 suppressed
+    int32_t *len;                              // live length of every candidate list (compacted round by round)
     int *changed;                              // [2]
     NmsCounters *ctr;
     unsigned int *qcount;                      // [2] queue fill, double buffered by round parity
@@ -490,29 +624,37 @@ nms_resolve_lazy_kernel(LazyParams P)
         // ---- phase A
         for (int r = gwarp; r < P.n; r += nwarps) {
             if (P.status[r] != 0) continue;
-            const int b = P.offs[r], e = P.offs[r + 1];
+            const int b = P.offs[r], e = b + P.len[r];
             bool pend = false, undec = false;
+            int outpos = b;                                  // in-place compaction: writes never pass the chunk being read
             for (int k0 = b; k0 < e; k0 += 32) {
                 const int k = k0 + lane;
                 bool need = false, un = false;
+                int j = -1;
                 if (k < e) {
-                    const int j = P.adj[k];
+                    j = P.adj[k];
                     if (j >= 0) {
                         const uint8_t st = P.status[j];
                         need = (st == 1);
                         un = (st == 0);
                     }
                 }
+                const bool live = need || un;
+                const unsigned lm = __ballot_sync(0xffffffffu, live);
+                const int mypos = outpos + __popc(lm & lt);
+                if (live) P.adj[mypos] = j;
                 const unsigned m = __ballot_sync(0xffffffffu, need);
                 if (m) {
                     unsigned int base = 0;
                     if (lane == 0) base = atomicAdd(qc, (unsigned int)__popc(m));
                     base = __shfl_sync(0xffffffffu, base, 0);
-                    if (need) P.queue[base + __popc(m & lt)] = make_int2(r, k);
+                    if (need) P.queue[base + __popc(m & lt)] = make_int2(r, mypos);
                     pend = true;
                 }
-                undec = undec || __any_sync(0xffffffffu, un);
+                undec = undec || (lm & ~m) != 0u;
+                outpos += __popc(lm);
             }
+            if (lane == 0) P.len[r] = outpos - b;
             if (pend) local = 1;
             else if (!undec) {
                 if (lane == 0) P.status[r] = 1;
@@ -563,13 +705,6 @@ nms_resolve_lazy_kernel(LazyParams P)
     if (tid == 0) P.ctr->rounds = round;
 }
 
-__global__ void __launch_bounds__(256)
-nms_slot_of_rank_kernel(const int32_t *__restrict__ rk, int n, int32_t *__restrict__ slot_of_rank)
-{
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n) slot_of_rank[rk[s]] = s;
-}
-
 // no-host-sync callers: make a candidate-list overflow visible on the device (the CSR is consistent but incomplete, so
 // boxes that should be suppressed could be kept): status_out = 1
 __global__ void nms_export_overflow_kernel(const NmsCounters *ctr, int32_t *status_out)
@@ -579,18 +714,17 @@ __global__ void nms_export_overflow_kernel(const NmsCounters *ctr, int32_t *stat
 
 __global__ void __launch_bounds__(256)
 nms_flags_kernel(const uint8_t *__restrict__ status, const int32_t *__restrict__ order,
-                 const int32_t *__restrict__ rank, const int32_t *__restrict__ slot_of_rank, int n, int out_order,
+                 const int32_t *__restrict__ rank, int by_orig, int n, int out_order,
                  uint8_t *__restrict__ flags, int64_t *__restrict__ vals)
 {
-    // status is indexed by rank (COMPAT32) or by sweep slot (EXACT64: slot_of_rank maps)
+    // status is indexed by rank (COMPAT32) or by original box index (EXACT64: by_orig)
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     if (out_order == ORP_ORDER_SCORE_DESC) {
-        flags[k] = status[slot_of_rank ? slot_of_rank[k] : k] == 1;
+        flags[k] = status[by_orig ? order[k] : k] == 1;      // k = rank, order[k] = its original index
         vals[k] = order[k];
     } else {
-        const int r = rank[k];
-        flags[k] = status[slot_of_rank ? slot_of_rank[r] : r] == 1;
+        flags[k] = status[by_orig ? k : rank[k]] == 1;
         vals[k] = k;
     }
 }
@@ -601,15 +735,7 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
             int order, int64_t *keep_out, int32_t *num_out, cudaStream_t st, uint8_t *flags_out, bool no_sync, int seg_limit,
             int32_t *overflow_out)
 {
-    // sweep keys are (segment << 32 | xmin); with a known segment bound only the low 32 + seg_bits bits need sorting
-    // (seg_bits chosen so that the all-ones field of non-finite boxes still sorts after every real segment)
     if (!segments) seg_limit = 1;
-    int sweep_bits = 64;
-    if (seg_limit > 0) {
-        int b = 1;
-        while ((1ll << b) <= (long long)seg_limit) ++b;
-        sweep_bits = 32 + b;
-    }
     if (n < 0 || (!flags_out && !num_out) || (n > 0 && (!dets || (!flags_out && !keep_out))))
         return fail(ORP_EINVAL, "orp_rnms: null pointer or negative n");
     if (iou_mode != ORP_NMS_EXACT64 && iou_mode != ORP_NMS_COMPAT32) return fail(ORP_EINVAL, "orp_rnms: bad iou_mode");
@@ -620,27 +746,44 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
         if (num_out) ORP_CUDA(cudaMemsetAsync(num_out, 0, sizeof(int32_t), st));
         return ORP_OK;
     }
+    const bool lazy = (iou_mode == ORP_NMS_EXACT64);
+    // Registration slots per box.  Large single sets (the poly_nms sweep: 10^5 boxes in one segment) are cut into y strips
+    // so that a box only meets the boxes of its own strips while walking its x interval; many small segments (a tile:
+    // 5 344 boxes per (image, class)) do not need them.  Segment ids must fit 15 bits next to the 16-bit strip index.
+    const long long per_seg = seg_limit > 0 ? (long long)n / seg_limit : (long long)n;
+    // (an unknown segment bound, seg_limit <= 0, keeps the strip-less layout whose key carries 31 segment bits)
+    const int R = (lazy && per_seg >= 16384 && seg_limit > 0 && seg_limit <= 32767 && !getenv("ORP_NMS_NO_STRIPS")) ? 4 : 1;
+    const int m = n * R;                                          // registration slots
+    // sweep keys: R == 1: (segment : xmin), R == 4: (segment(15) : strip(16) : xmin); only the bits in use are sorted -
+    // enough of them that the all-ones keys of padding / non-finite boxes still sort after every real key
+    int sweep_bits = 64;
+    if (seg_limit > 0) {
+        int sb = 1;
+        while ((1ll << sb) <= (long long)seg_limit) ++sb;
+        sweep_bits = (R == 1 ? 32 : 48) + sb;
+        if (sweep_bits > 64) sweep_bits = 64;
+    }
     Scratch S(st);
-    const int T = 256, G = ceil_div(n, T);
+    const int T = 256, G = ceil_div(n, T), GM = ceil_div(m, T);
     uint32_t *score_key = S.get<uint32_t>(n), *score_key2 = S.get<uint32_t>(n);
-    uint64_t *sweep_key = S.get<uint64_t>(n), *sweep_key2 = S.get<uint64_t>(n);
-    int32_t *iota = S.get<int32_t>(n), *order_r = S.get<int32_t>(n), *perm = S.get<int32_t>(n);
+    uint64_t *sweep_key = S.get<uint64_t>(m), *sweep_key2 = S.get<uint64_t>(m);
+    int32_t *iota = S.get<int32_t>(m), *order_r = S.get<int32_t>(n), *perm = S.get<int32_t>(m);
     int32_t *rank = S.get<int32_t>(n);
-    float4 *aabb = S.get<float4>(n), *v01 = S.get<float4>(n), *v23 = S.get<float4>(n);
-    int32_t *rk = S.get<int32_t>(n), *sg = S.get<int32_t>(n), *nvalid = S.get<int32_t>(1);
+    float4 *aabb = S.get<float4>(m), *v01 = S.get<float4>(n), *v23 = S.get<float4>(n), *baabb = S.get<float4>(n);
+    int32_t *rk = S.get<int32_t>(m), *sg = S.get<int32_t>(m), *nvalid = S.get<int32_t>(1);
     float *area = S.get<float>(n);
     int32_t *indeg = S.get<int32_t>(n + 1), *offs = S.get<int32_t>(n + 1), *cursor = S.get<int32_t>(n + 1);
     uint8_t *status = S.get<uint8_t>(n), *flags = S.get<uint8_t>(n);
     int64_t *vals = S.get<int64_t>(n);
     int *changed = S.get<int>(2);
     unsigned int *qcount = S.get<unsigned int>(2);
-    int32_t *slot_of_rank = S.get<int32_t>(n);
+    NmsGlobal *glob = S.get<NmsGlobal>(1);
     NmsCounters *ctr = S.get<NmsCounters>(1);
-    if (!ctr || !vals || !changed || !qcount || !slot_of_rank) return fail(ORP_ECUDA, "orp_rnms: scratch allocation failed");
+    if (!ctr || !vals || !changed || !qcount || !glob) return fail(ORP_ECUDA, "orp_rnms: scratch allocation failed");
 
     size_t tb1 = 0, tb2 = 0, tb3 = 0, tb4 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb1, score_key, score_key2, iota, order_r, n, 0, 32, st);
-    cub::DeviceRadixSort::SortPairs(nullptr, tb2, sweep_key, sweep_key2, iota, perm, n, 0, sweep_bits, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb2, sweep_key, sweep_key2, iota, perm, m, 0, sweep_bits, st);
     cub::DeviceScan::ExclusiveSum(nullptr, tb3, indeg, offs, n + 1, st);
     if (keep_out && num_out) cub::DeviceSelect::Flagged(nullptr, tb4, vals, flags, keep_out, num_out, n, st);
     size_t tb = tb1 > tb2 ? tb1 : tb2;
@@ -655,8 +798,15 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
     ORP_CUDA(cudaMemsetAsync(status, 0, (size_t)n, st));
     ORP_CUDA(cudaMemsetAsync(changed, 0, 2 * sizeof(int), st));
     ORP_CUDA(cudaMemsetAsync(qcount, 0, 2 * sizeof(unsigned int), st));
+    {
+        NmsGlobal g0;
+        g0.ymin_key = 0xFFFFFFFFu; g0.maxh_bits = 0u; g0.sumh = 0.0; g0.count = 0u;
+        static thread_local NmsGlobal g0_host;                    // source of an async copy must outlive the call
+        g0_host = g0;
+        ORP_CUDA(cudaMemcpyAsync(glob, &g0_host, sizeof(NmsGlobal), cudaMemcpyHostToDevice, st));
+    }
 
-    nms_prep_kernel<<<G, T, 0, st>>>(dets, segments, n, score_key, sweep_key, iota);
+    nms_prep_kernel<<<G, T, 0, st>>>(dets, segments, n, score_key, lazy ? nullptr : sweep_key, iota);
     ORP_LAUNCHED();
     ORP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb1, score_key, score_key2, iota, order_r, n, 0, 32, st));
     count_launches(4);
@@ -673,16 +823,19 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
     for (int attempt = 0; attempt < 6; ++attempt) {
         int2 *edges = S.get<int2>(cap);
         if (!edges) return fail(ORP_ECUDA, "orp_rnms: edge buffer allocation failed");
-        if (iou_mode == ORP_NMS_EXACT64) {
+        if (lazy) {
             if (attempt == 0) {
-                ORP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb2, sweep_key, sweep_key2, iota, perm, n, 0, sweep_bits, st));
+                nms_boxes_kernel<<<G, T, 0, st>>>(dets, n, baabb, v01, v23, area, glob);
+                ORP_LAUNCHED();
+                nms_regs_kernel<<<G, T, 0, st>>>(baabb, segments, n, R, glob, sweep_key, iota);
+                ORP_LAUNCHED();
+                ORP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb2, sweep_key, sweep_key2, iota, perm, m, 0, sweep_bits, st));
                 count_launches((sweep_bits + 7) / 8);
-                nms_gather_kernel<<<G, T, 0, st>>>(dets, segments, perm, sweep_key2, rank, n, aabb, v01, v23,
-                                                   rk, sg, area, nvalid);
+                nms_slots_kernel<<<GM, T, 0, st>>>(sweep_key2, perm, baabb, m, aabb, sg, rk, nvalid);   // sg = group, rk = box id
                 ORP_LAUNCHED();
             }
-            SweepParams P{aabb, v01, v23, rk, sg, area, nvalid, edges, indeg, cap, ctr, thr, union_mode};
-            int grid = ceil_div(n, kSweepWarps);
+            SweepParams P{aabb, sg, rk, v01, v23, area, rank, nvalid, glob, R, edges, indeg, cap, ctr, thr, union_mode};
+            int grid = ceil_div(m, kSweepWarps);
             const int maxgrid = 148 * 8 * 4;
             if (grid > maxgrid) grid = maxgrid;
             if (g_timing) {
@@ -730,21 +883,19 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
         nms_scatter_kernel<<<grid, 256, 0, st>>>(edges, ctr, cap, offs, cursor, adj);
         ORP_LAUNCHED();
     }
-    const bool lazy = (iou_mode == ORP_NMS_EXACT64);
     {
         int dev = 0, sms = 0, per_sm = 0;
         ORP_CUDA(cudaGetDevice(&dev));
         ORP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         if (lazy) {
-            nms_slot_of_rank_kernel<<<G, T, 0, st>>>(rk, n, slot_of_rank);
-            ORP_LAUNCHED();
             ORP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_resolve_lazy_kernel, 256, 0));
             if (per_sm > 4) per_sm = 4;
             int grid = sms * (per_sm > 0 ? per_sm : 1);
             int need = ceil_div(n, 8);                       // a warp per box in the scan phase
             if (grid > need) grid = need;
-            // the candidate buffer is free once scattered into the CSR: it becomes the work queue
-            LazyParams LP{offs, adj, n, status, changed, ctr, qcount, edges, aabb, v01, v23, area, thr, union_mode};
+            // the candidate buffer is free once scattered into the CSR: it becomes the work queue; after the scatter
+            // `cursor` holds every list's length
+            LazyParams LP{offs, adj, n, status, cursor, changed, ctr, qcount, edges, baabb, v01, v23, area, thr, union_mode};
             void *args[] = {&LP};
             ORP_CUDA(cudaLaunchCooperativeKernel((void *)nms_resolve_lazy_kernel, dim3(grid), dim3(256), args, 0, st));
             ORP_LAUNCHED();
@@ -768,8 +919,9 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
         nms_export_overflow_kernel<<<1, 1, 0, st>>>(ctr, overflow_out);
         ORP_LAUNCHED();
     }
-    nms_flags_kernel<<<G, T, 0, st>>>(status, order_r, rank, lazy ? slot_of_rank : nullptr, n,
-                                      flags_out ? ORP_ORDER_INDEX_ASC : order, flags_out ? flags_out : flags, vals);
+    // EXACT64: status is indexed by original box index; COMPAT32: by rank
+    nms_flags_kernel<<<G, T, 0, st>>>(status, order_r, rank, lazy ? 1 : 0, n, flags_out ? ORP_ORDER_INDEX_ASC : order,
+                                      flags_out ? flags_out : flags, vals);
     ORP_LAUNCHED();
     if (keep_out && num_out) {
         if (flags_out && order != ORP_ORDER_INDEX_ASC) return fail(ORP_EINVAL, "orp_rnms: flags_out needs index order");

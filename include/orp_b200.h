@@ -89,8 +89,10 @@ int orp_rnms(const float *dets, const int32_t *segments, int n, double iou_thr, 
 
 /* Drop-in for `void _poly_nms(int* keep_out, int* num_out, const float* polys_host,
  * int polys_num, int polys_dim, float nms_overlap_thresh, int device_id)`
- * (DOTA_devkit/poly_nms_gpu/poly_nms.hpp:9-10).  polys_host must ALREADY be sorted by score
- * descending as poly_nms.pyx:19-21 does; keep_out receives positions in that order.
+ * (DOTA_devkit/poly_nms_gpu/poly_nms.hpp:9-10).  The reference's caller sorts polys_host by score
+ * descending first (poly_nms.pyx:19-21) and gets positions in that order; this entry orders by score
+ * itself (ties: lower row first), so sorted input gives exactly those positions and unsorted input gives
+ * the same boxes as original row indices - the host sort can be dropped.
  * Host buffers, blocking.  polys_dim must be 9.  Unlike the reference, device_id is honoured. */
 int orp_poly_nms_host(int *keep_out, int *num_out, const float *polys_host, int polys_num,
                       int polys_dim, float nms_overlap_thresh, int device_id);

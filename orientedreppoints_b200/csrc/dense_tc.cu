@@ -1392,6 +1392,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     if (P.tma_epi) staging = P.epi_bufs * (P.epi_merge ? 32768 : 16384) * (P.epi_split ? 2 : 1);
     int stages = (int)((227 * 1024 - 4096 - 1024 - staging - bres_bytes) / stage_bytes);
     if (stages > kStagesMax) stages = kStagesMax;
+    if (const char *e = getenv("ORP_TC_STAGES")) { const int v = atoi(e); if (v >= 2 && v < stages) stages = v; }   // experiments
     if (deform && stages > 3) stages = 3;     // leave L1 capacity for the bilinear gather (corner reuse between neighbouring pixels)
     int lrc = ORP_EINVAL;
     bool launched = false;

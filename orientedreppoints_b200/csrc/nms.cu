@@ -599,7 +599,9 @@ struct LazyParams {
     int *changed;                              // [2]
     NmsCounters *ctr;
     unsigned int *qcount;                      // [2] queue fill, double buffered by round parity
-    int2 *queue;                               // (box slot, adj position); capacity = number of candidates
+    int2 *queue;                               // (box, adj position); capacity = number of candidates
+    unsigned int *wcount;                      // [2] worklist fill (boxes still undecided after a round), same parity scheme
+    int32_t *worklist;                         // [2][n]
     const float4 *aabb, *v01, *v23;
     const float *area;
     double thr;
@@ -621,8 +623,12 @@ nms_resolve_lazy_kernel(LazyParams P)
         int *flag = &P.changed[round & 1];
         unsigned int *qc = &P.qcount[round & 1];
         int local = 0;
-        // ---- phase A
-        for (int r = gwarp; r < P.n; r += nwarps) {
+        // ---- phase A: round 0 visits every box, later rounds only the boxes the previous round left undecided
+        const unsigned int nsrc = round == 0 ? (unsigned int)P.n : *(volatile unsigned int *)&P.wcount[(round - 1) & 1];
+        const int32_t *src = P.worklist + (size_t)((round - 1) & 1) * P.n;
+        int32_t *dst = P.worklist + (size_t)(round & 1) * P.n;
+        for (unsigned int w = gwarp; w < nsrc; w += nwarps) {
+            const int r = round == 0 ? (int)w : src[w];
             if (P.status[r] != 0) continue;
             const int b = P.offs[r], e = b + P.len[r];
             bool pend = false, undec = false;
@@ -660,13 +666,14 @@ nms_resolve_lazy_kernel(LazyParams P)
                 if (lane == 0) P.status[r] = 1;
                 local = 1;
             }
+            if ((pend || undec) && lane == 0) dst[atomicAdd(&P.wcount[round & 1], 1u)] = r;
         }
         if (local) *flag = 1;
         __threadfence();
         grid.sync();
         const int any = *(volatile int *)flag;
         const unsigned int nq = *(volatile unsigned int *)qc;
-        if (tid == 0) { P.changed[(round + 1) & 1] = 0; P.qcount[(round + 1) & 1] = 0; }
+        if (tid == 0) { P.changed[(round + 1) & 1] = 0; P.qcount[(round + 1) & 1] = 0; P.wcount[(round + 1) & 1] = 0; }
         // ---- phase B
         for (unsigned int q = tid; q < nq; q += nth) {
             const int2 e = P.queue[q];
@@ -776,10 +783,11 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
     uint8_t *status = S.get<uint8_t>(n), *flags = S.get<uint8_t>(n);
     int64_t *vals = S.get<int64_t>(n);
     int *changed = S.get<int>(2);
-    unsigned int *qcount = S.get<unsigned int>(2);
+    unsigned int *qcount = S.get<unsigned int>(4);                // [0..1] queue fill, [2..3] worklist fill
+    int32_t *worklist = lazy ? S.get<int32_t>(2 * (size_t)n) : nullptr;
     NmsGlobal *glob = S.get<NmsGlobal>(1);
     NmsCounters *ctr = S.get<NmsCounters>(1);
-    if (!ctr || !vals || !changed || !qcount || !glob) return fail(ORP_ECUDA, "orp_rnms: scratch allocation failed");
+    if (!ctr || !vals || !changed || !qcount || !glob || (lazy && !worklist)) return fail(ORP_ECUDA, "orp_rnms: scratch allocation failed");
 
     size_t tb1 = 0, tb2 = 0, tb3 = 0, tb4 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb1, score_key, score_key2, iota, order_r, n, 0, 32, st);
@@ -797,7 +805,7 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
     ORP_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)(n + 1), st));
     ORP_CUDA(cudaMemsetAsync(status, 0, (size_t)n, st));
     ORP_CUDA(cudaMemsetAsync(changed, 0, 2 * sizeof(int), st));
-    ORP_CUDA(cudaMemsetAsync(qcount, 0, 2 * sizeof(unsigned int), st));
+    ORP_CUDA(cudaMemsetAsync(qcount, 0, 4 * sizeof(unsigned int), st));
     {
         NmsGlobal g0;
         g0.ymin_key = 0xFFFFFFFFu; g0.maxh_bits = 0u; g0.sumh = 0.0; g0.count = 0u;
@@ -895,7 +903,7 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
             if (grid > need) grid = need;
             // the candidate buffer is free once scattered into the CSR: it becomes the work queue; after the scatter
             // `cursor` holds every list's length
-            LazyParams LP{offs, adj, n, status, cursor, changed, ctr, qcount, edges, baabb, v01, v23, area, thr, union_mode};
+            LazyParams LP{offs, adj, n, status, cursor, changed, ctr, qcount, edges, qcount + 2, worklist, baabb, v01, v23, area, thr, union_mode};
             void *args[] = {&LP};
             ORP_CUDA(cudaLaunchCooperativeKernel((void *)nms_resolve_lazy_kernel, dim3(grid), dim3(256), args, 0, st));
             ORP_LAUNCHED();

@@ -19,19 +19,16 @@ def poly_gpu_nms(dets, thresh, device_id=0):
     boxes_num, boxes_dim = dets.shape
     if boxes_num == 0:
         return []
-    scores = dets[:, 8]
-    # poly_nms.pyx:19 uses scores.argsort()[::-1]; ties are implementation-defined there, we break
-    # them by lower index first (same as the device path)
-    order = np.argsort(-scores, kind='stable')
-    sorted_dets = np.ascontiguousarray(dets[order, :])
-    keep = np.zeros(boxes_num, dtype=np.int32)
+    # poly_nms.pyx:19-21 sorts on the host (scores.argsort()[::-1]) and hands `_poly_nms` the sorted rows.  The device path
+    # orders by score itself (ties: lower row first, what a stable host sort gives), so the rows go down unsorted and the
+    # kept ORIGINAL indices come back in score order - the same list, without a 100k-element host sort per call.
+    keep = np.empty(boxes_num, dtype=np.int32)
     num_out = ctypes.c_int(0)
     rc = _lib.lib().orp_poly_nms_host(keep.ctypes.data_as(ctypes.c_void_p), ctypes.addressof(num_out),
-                                      sorted_dets.ctypes.data_as(ctypes.c_void_p), boxes_num, boxes_dim,
+                                      dets.ctypes.data_as(ctypes.c_void_p), boxes_num, boxes_dim,
                                       float(thresh), int(device_id))
     _lib.check(rc, "orp_poly_nms_host")
-    keep = keep[:num_out.value]
-    return list(order[keep])
+    return keep[:num_out.value].tolist()
 
 
 def poly_overlaps(boxes, query_boxes, device_id=0):

@@ -28,7 +28,13 @@
 // stored [N,H,W,2,C]: hi channels then lo channels per pixel) and every product is evaluated as
 // hi*hi + lo*hi + hi*lo with three MMAs into the same fp32 TMEM accumulator (the dropped lo*lo term is 2^-22
 // relative) - fp32-faithful arithmetic at 1/3 of the tensor-pipe rate; this is the parity mode.  The K loop
-// simply runs three "terms" per (tap, channel block); weights are stored [Cout][tap][2][Cin] = (hi, lo).
+// simply runs three "terms" per (tap, channel block); weights are stored [Cout][tap][channel block][2][64] = (hi, lo).
+// A tcgen05.mma with M = 128 takes the same ~100 ns whatever N <= 256 (measured: 87 / 97 / 115 ns at N = 64 / 128 / 256), so
+// layers with 64 or 128 output channels are issue-bound at a quarter / half of the tensor rate.  For those (BN <= 128) the
+// terms are concatenated along N instead of K ("ncat"): per K step  x_hi * [w_hi | w_lo]  is ONE MMA of width 2 BN (main
+// product into accumulator columns [0, BN), cross term into [BN, 2 BN)) and  x_lo * w_hi  a second one into [BN, 2 BN) -
+// two instructions instead of three, the x_hi / x_lo tiles of a (tap, channel block) are loaded once, and the small cross
+// terms own an accumulator (their sum never meets the large main sum before the epilogue adds the two in fp32).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -87,6 +93,7 @@ struct alignas(64) TcParams {
     Problem prob[kMaxProb];
     int tma_epi, epi_bufs;                    // TMA epilogue on/off; output staging buffers (1 or 2)
     int epi_merge;                            // split mode, memory-bound layers: hi and lo tiles of a 64-column group leave in ONE pass
+    int ncat;                                 // split mode, BN <= 128: terms concatenated along N (see the kernel header)
     int b_resident;                           // short-K layers: the whole weight slab of this CTA's N tile stays in shared memory
     int res_mma;                              // residual added by the tensor core: extra K blocks  R[128x64] * I[64x64]
     int epi_split;                            // epilogue-bound layers: the two epilogue warpgroups work on alternate tiles (one per accumulator buffer)
@@ -332,7 +339,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kBBytes = BN * kBK * 2;
     // b_resident: [B slab: kblocks x kBBytes] then A-only stages; otherwise every stage carries A | B
-    const int kStageBytes = P.b_resident ? kABytes : kABytes + kBBytes;
+    const int kStageBytes = P.ncat ? (P.b_resident ? 2 * kABytes : 2 * kABytes + 2 * kBBytes)
+                                   : (P.b_resident ? kABytes : kABytes + kBBytes);
     const int kblocks_all = P.KH * P.KW * P.cin_blocks * (P.split ? 2 : 1);   // weight K blocks (hi and lo halves in split mode)
     uint8_t *ident = smem;                             // [8 KiB] identity block when res_mma
     if (P.res_mma) smem += 8192;
@@ -352,7 +360,9 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     uint32_t *tmem_slot = &tmem_slot_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    // two accumulator buffers; BN <= 128 leaves room for the ncat layout (main | cross columns per buffer)
+    constexpr uint32_t kAccCols = BN <= 128 ? 4 * BN : 2 * BN;
+    constexpr uint32_t kTmemCols = (kAccCols <= 32) ? 32 : (kAccCols <= 64) ? 64 : (kAccCols <= 128) ? 128 : (kAccCols <= 256) ? 256 : 512;
 
     if (warp == 0 && elect_one()) {
 #pragma unroll 1
@@ -378,7 +388,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int kblocks = P.KH * P.KW * P.cin_blocks * (P.split ? 3 : 1);       // main-loop K blocks per tile
+    const int kblocks = P.KH * P.KW * P.cin_blocks * ((P.split && !P.ncat) ? 3 : 1);   // main-loop K blocks (stages) per tile
     // Programmatic dependent launch: the next kernel in the stream may start its CTAs (barrier init, TMEM allocation,
     // descriptor prefetch - the code above) on SMs this grid has already left; nothing above touches global memory,
     // and everything below (loads AND stores) comes after the wait for the preceding grid to complete and flush.
@@ -404,16 +414,27 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 decode_tile(P, tile, pi, wb, hb, ib, nt);
                 const Problem &pr = P.prob[pi];
                 const int w0 = wb * pr.BW * P.stride - P.pad, h0 = hb * pr.BH * P.stride - P.pad, i0 = ib * pr.BI;
-                KIter it(P.KH * P.KW, P.cin_blocks, P.split ? (DEFORM ? 2 : 1) : 0);
+                KIter it(P.KH * P.KW, P.cin_blocks, (P.split && !P.ncat) ? (DEFORM ? 2 : 1) : 0);
                 for (int j = 0; j < kblocks; ++j, it.next()) {
                     const int kh = it.tap / P.KW, kw = it.tap - kh * P.KW;
                     mbar_wait(&empty[r.stage], r.phase ^ 1);
                     uint8_t *sa = smem + (size_t)r.stage * kStageBytes;
-                    mbar_expect_tx(&full[r.stage], DEFORM ? kBBytes : (P.b_resident ? kABytes : kABytes + kBBytes));
-                    if (!DEFORM) tma_load_5d(sa, &P.tmA[pi], &full[r.stage], it.cb * kBK, it.term == 1 ? 1 : 0, w0 + kw, h0 + kh, i0);
-                    if (!P.b_resident)
-                        tma_load_2d(sa + kABytes, &P.tmB, &full[r.stage],
-                                    ((it.tap * wterms + (it.term == 2 ? 1 : 0)) * P.cin_blocks + it.cb) * kBK, nt * BN);
+                    const int wblk = ((it.tap * P.cin_blocks + it.cb) * wterms) * kBK;      // K offset of the (hi, lo) weight blocks
+                    if (P.ncat) {
+                        // one stage = x_hi tile | x_lo tile | w_hi block | w_lo block of this (tap, channel block)
+                        mbar_expect_tx(&full[r.stage], P.b_resident ? 2 * kABytes : 2 * kABytes + 2 * kBBytes);
+                        tma_load_5d(sa, &P.tmA[pi], &full[r.stage], it.cb * kBK, 0, w0 + kw, h0 + kh, i0);
+                        tma_load_5d(sa + kABytes, &P.tmA[pi], &full[r.stage], it.cb * kBK, 1, w0 + kw, h0 + kh, i0);
+                        if (!P.b_resident) {
+                            tma_load_2d(sa + 2 * kABytes, &P.tmB, &full[r.stage], wblk, nt * BN);
+                            tma_load_2d(sa + 2 * kABytes + kBBytes, &P.tmB, &full[r.stage], wblk + kBK, nt * BN);
+                        }
+                    } else {
+                        mbar_expect_tx(&full[r.stage], DEFORM ? kBBytes : (P.b_resident ? kABytes : kABytes + kBBytes));
+                        if (!DEFORM) tma_load_5d(sa, &P.tmA[pi], &full[r.stage], it.cb * kBK, it.term == 1 ? 1 : 0, w0 + kw, h0 + kh, i0);
+                        if (!P.b_resident)
+                            tma_load_2d(sa + kABytes, &P.tmB, &full[r.stage], wblk + (it.term == 2 ? kBK : 0), nt * BN);
+                    }
                     r.next();
                 }
                 if (!DEFORM && P.res_mma) {
@@ -436,6 +457,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
         const uint32_t fmt = P.split ? 0u : 1u;
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
         const uint32_t idesc64 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        const uint32_t idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)((2 * BN > 256 ? 256 : 2 * BN) >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);   // N = 2 BN (ncat)
         Ring r(stages);
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -449,19 +471,31 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
             }
             mbar_wait(&tempty[acc], acc_phase ^ 1);
             tcgen05_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-            KIter it(P.KH * P.KW, P.cin_blocks, P.split ? (DEFORM ? 2 : 1) : 0);   // same walk as the producer (resident weights: slab index)
+            const uint32_t accw = P.ncat ? 2u * BN : (uint32_t)BN;          // TMEM columns of one accumulator buffer
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * accw;
+            KIter it(P.KH * P.KW, P.cin_blocks, (P.split && !P.ncat) ? (DEFORM ? 2 : 1) : 0);   // same walk as the producer
             for (int kb = 0; kb < kblocks; ++kb, it.next()) {
                 mbar_wait(&full[r.stage], r.phase);
                 tcgen05_fence_after();
                 if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + (size_t)r.stage * kStageBytes);
                     const uint64_t da = make_desc_sw128(sa);
-                    const int slab = (it.tap * wterms + (it.term == 2 ? 1 : 0)) * P.cin_blocks + it.cb;
-                    const uint64_t db = make_desc_sw128(P.b_resident ? smem_u32(bres + (size_t)slab * kBBytes) : sa + kABytes);
+                    const int slab = (it.tap * P.cin_blocks + it.cb) * wterms + (it.term == 2 ? 1 : 0);
+                    if (P.ncat) {
+                        // [w_hi | w_lo] are adjacent in the stage (and in the resident slab): one operand of 2 BN rows
+                        const uint64_t dl = make_desc_sw128(sa + kABytes);
+                        const uint64_t db = make_desc_sw128(P.b_resident ? smem_u32(bres + (size_t)slab * kBBytes) : sa + 2 * kABytes);
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k)
-                        umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < kBK / 16; ++k) {
+                            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc2, (kb | k) ? 1u : 0u);        // x_hi * [w_hi | w_lo]
+                            umma_bf16(d_tmem + (uint32_t)BN, dl + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);          // x_lo * w_hi -> cross columns
+                        }
+                    } else {
+                        const uint64_t db = make_desc_sw128(P.b_resident ? smem_u32(bres + (size_t)slab * kBBytes) : sa + kABytes);
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k)
+                            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    }
                     umma_commit(&empty[r.stage]);
                     if (kb == kblocks - 1 && res_groups == 0) umma_commit(&tfull[acc]);
                 }
@@ -579,12 +613,21 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
 #pragma unroll 1
                     for (int ch = ch0; ch < 2; ch += chs) {
                         uint32_t v[32];
-                        tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * 64 + ch * 32), v);
+                        const uint32_t accw = P.ncat ? 2u * BN : (uint32_t)BN;
+                        const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * accw + (uint32_t)(half * 64 + ch * 32);
+                        tmem_ld32_issue(tcol, v);
                         // bias slice of these 32 columns: eight back-to-back shared loads, in flight with the TMEM load
                         uint4 bu[8];
 #pragma unroll
                         for (int j8 = 0; j8 < 8; ++j8) bu[j8] = lds128(bias_u + (uint32_t)(half * 64 + ch * 32 + j8 * 4) * 4u);
                         tmem_ld_wait(v);
+                        if (P.ncat) {
+                            // main + cross accumulators meet here, in fp32 with round-to-nearest
+                            uint32_t vc[32];
+                            tmem_ld32(tcol + (uint32_t)BN, vc);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(vc[j]));
+                        }
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
                             const int c16 = ch * 4 + j4;                  // 16-byte chunk inside the 128-byte row
@@ -1060,7 +1103,9 @@ thread_local TcTrace g_tc_trace[kEvPool];
 template <int BN, bool OUT_F32, bool DEFORM>
 int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st, int staging_bytes)
 {
-    const size_t smem = 1024 + (size_t)stages * (P.b_resident ? kABytes : kABytes + BN * kBK * 2) + (size_t)staging_bytes;
+    const size_t stage_b = P.ncat ? (P.b_resident ? 2 * kABytes : 2 * kABytes + 2 * BN * kBK * 2)
+                                  : (P.b_resident ? kABytes : kABytes + BN * kBK * 2);
+    const size_t smem = 1024 + (size_t)stages * stage_b + (size_t)staging_bytes;
     auto kern = conv_tc_kernel<BN, OUT_F32, DEFORM>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1295,7 +1340,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
         }
     }
     {
-        // weights [Cout_padded][tap][T][cin_blocks x 64] (zero padded per tap; T = 2: hi then lo)
+        // weights [Cout_padded][tap][cin_blocks][T][64] (zero padded per tap; T = 2: the hi block, then the lo block)
         const cuuint64_t K = (cuuint64_t)KH * KW * T * P.cin_blocks * kBK;
         cuuint64_t gdim[2] = {K, (cuuint64_t)Cout_padded};
         cuuint64_t gstr[1] = {K * 2};
@@ -1326,10 +1371,13 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     P.epi_bufs = mem_bound ? 2 : 1;          // a second staging tile costs compute-bound layers a main-loop stage
     if (const char *e = getenv("ORP_TC_EPI_BUFS")) P.epi_bufs = atoi(e) == 1 ? 1 : 2;
     P.epi_merge = (split && P.tma_epi && (mem_bound || stem == 2) && !getenv("ORP_TC_NO_MERGE")) ? 1 : 0;
+    // terms concatenated along N for narrow layers (kernel header); the residual / deformable / fp32-output variants keep
+    // the K-concatenated walk
+    P.ncat = (split && P.tma_epi && BN <= 128 && !deform && !any_res && stem != 1 && !getenv("ORP_TC_NO_NCAT")) ? 1 : 0;
     // epilogue-bound layers (at most 6 K blocks per tile incl. the residual's; measured: 7-15 lose a little to the
     // smaller staging/stage budget): independent epilogue warpgroups
     {
-        const int kb_total = (KH * KW * P.cin_blocks) * (split ? 3 : 1) + (any_res ? (BN / 64) * T : 0);
+        const int kb_total = (KH * KW * P.cin_blocks) * ((split && !P.ncat) ? 3 : 1) + (any_res ? (BN / 64) * T : 0);
         P.epi_split = (P.tma_epi && !deform && !stem && kb_total <= 6 && !getenv("ORP_TC_NO_SPLIT")) ? 1 : 0;
         if (P.epi_split) P.epi_bufs = 2;
     }
@@ -1385,12 +1433,24 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     int grid = P.num_tiles < sms ? P.num_tiles : sms;
     if (P.b_resident && grid >= P.n_tiles_n) grid -= grid % P.n_tiles_n;       // fixed N tile per CTA
     else if (P.b_resident) P.b_resident = 0;
-    const int stage_bytes = P.b_resident ? kABytes : kABytes + BN * kBK * 2;
-    const int bres_bytes = (P.b_resident ? KH * KW * T * P.cin_blocks * BN * kBK * 2 : 0) + (P.res_mma ? 8192 : 0);
-    const int hc = BN < 64 ? BN : 64;
-    int staging = out_f32 ? 0 : 128 * (hc * 2 + 16);
-    if (P.tma_epi) staging = P.epi_bufs * (P.epi_merge ? 32768 : 16384) * (P.epi_split ? 2 : 1);
-    int stages = (int)((227 * 1024 - 4096 - 1024 - staging - bres_bytes) / stage_bytes);
+    // shared-memory budget: output staging + resident weights + main-loop stages.  When the extras leave fewer than three
+    // stages they are given up in order of least value: the second epilogue group, the second staging slot, the resident slab.
+    int stage_bytes = 0, bres_bytes = 0, staging = 0, stages = 0;
+    for (;;) {
+        stage_bytes = P.ncat ? (P.b_resident ? 2 * kABytes : 2 * kABytes + 2 * BN * kBK * 2)
+                             : (P.b_resident ? kABytes : kABytes + BN * kBK * 2);
+        bres_bytes = (P.b_resident ? KH * KW * T * P.cin_blocks * BN * kBK * 2 : 0) + (P.res_mma ? 8192 : 0);
+        const int hc = BN < 64 ? BN : 64;
+        staging = out_f32 ? 0 : 128 * (hc * 2 + 16);
+        if (P.tma_epi) staging = P.epi_bufs * (P.epi_merge ? 32768 : 16384) * (P.epi_split ? 2 : 1);
+        stages = (int)((227 * 1024 - 4096 - 1024 - staging - bres_bytes) / stage_bytes);
+        if (stages >= 3) break;
+        if (P.epi_split) { P.epi_split = 0; P.epi_bufs = mem_bound ? 2 : 1; continue; }
+        if (P.epi_bufs == 2) { P.epi_bufs = 1; continue; }
+        if (P.b_resident) { P.b_resident = 0; continue; }
+        if (stages >= 2) break;
+        return fail(ORP_EINVAL, "conv2d_tc: shared-memory budget cannot hold two main-loop stages");
+    }
     if (stages > kStagesMax) stages = kStagesMax;
     if (const char *e = getenv("ORP_TC_STAGES")) { const int v = atoi(e); if (v >= 2 && v < stages) stages = v; }   // experiments
     if (deform && stages > 3) stages = 3;     // leave L1 capacity for the bilinear gather (corner reuse between neighbouring pixels)

@@ -247,7 +247,8 @@ class EngineTCSplit(EngineTC):
             wp4 = torch.zeros((cout_p, kh * kw, cin_p), dtype=torch.float32)
             wp4[:cout, :, :cin] = w.reshape(cout, kh * kw, cin)
             hi, lo, s = self._split_weights(wp4)
-            wp = torch.stack([hi, lo], dim=2)                        # [cout_p, taps, 2, cin_p]
+            cbn = cin_p // 64                                        # [cout_p, taps, channel block, (hi, lo), 64]: the two halves
+            wp = torch.stack([hi.reshape(cout_p, kh * kw, cbn, 64), lo.reshape(cout_p, kh * kw, cbn, 64)], dim=3)   # of a block are adjacent
             L.tc3 = dict(w=wp.reshape(cout_p, -1).to(self.device).contiguous(), cout_p=cout_p, s=s)
         return L.tc3
 

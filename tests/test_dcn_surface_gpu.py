@@ -110,11 +110,15 @@ def test_config_built_detector_runs_on_engine(cuda):
     ref = eng.simple_test(img, [dict(scale_factor=1.0)], rescale=True)
     assert len(res) == 1 and len(res[0]) == 15
     # GroupNorm statistics are accumulated with atomics: two passes agree to the last bits, not bit for bit, so a candidate
-    # sitting exactly on a threshold may fall either way - compare class by class with that allowance
-    na, nb, same = 0, 0, 0
-    for a, b in zip(res[0], ref[0]):
-        na, nb = na + a.shape[0], nb + b.shape[0]
-        assert abs(a.shape[0] - b.shape[0]) <= 2
-        if a.shape == b.shape and a.shape[0]:
-            same += int((abs(a - b).max(axis=1) < 1e-2).sum())
-    assert na > 10 and abs(na - nb) <= max(2, na // 100) and same > 0.9 * na
+    # sitting exactly on a threshold may fall either way - match detections by content (class + coordinates), not by position
+    import numpy as np
+
+    def flat(r):
+        rows = [np.concatenate([a, np.full((a.shape[0], 1), c, np.float32)], 1) for c, a in enumerate(r) if a.shape[0]]
+        return torch.from_numpy(np.concatenate(rows, 0)) if rows else torch.zeros((0, 28))
+
+    fa, fb = flat(res[0]), flat(ref[0])
+    assert fa.shape[0] > 10 and abs(fa.shape[0] - fb.shape[0]) <= max(2, fa.shape[0] // 50)
+    d = torch.cdist(fa[:, :26].double(), fb[:, :26].double(), p=float("inf")) + (fa[:, 27:28] != fb[:, 27:28].T).double() * 1e6
+    assert float((d.min(dim=1).values < 1e-2).float().mean()) > 0.97
+    assert float((d.min(dim=0).values < 1e-2).float().mean()) > 0.97

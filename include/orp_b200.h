@@ -196,6 +196,15 @@ int orp_head_postprocess(int nlevels, const float *const *cls, const float *cons
                          const int *W, const int *stride, int B, int num_cls, int nms_pre, float score_thr,
                          double iou_thr, int max_per_img, const float *scale_factor, float *dets_out,
                          int64_t *labels_out, int32_t *counts_out, void *stream);
+/* padded detections of orp_head_postprocess -> the fixed-layout payload of the ONE all-gather that replaces
+ * collect_results_gpu (mmdet/apis/test.py:117-147): packed_out device fp32 [B, max_per_img + 1, 28], rows = 27 detection values |
+ * label, zero padded; row max_per_img carries the image's count in column 0. */
+int orp_pack_detections(const float *dets, const int64_t *labels, const int32_t *counts, int B, int max_per_img,
+                        float *packed_out, void *stream);
+/* orientedreppoints_head.py:162-163 for up to 8 pyramid levels in one launch: off = (1 - g) * pts + g * pts - base[c],
+ * pts / off fp32 [.., 18] (host arrays of device pointers, element counts), base18 = the 3x3 grid (dy,dx) of :82-88 (host) */
+int orp_dcn_offsets_multi(int nprob, const float *const *pts, float *const *off, const long long *numel,
+                          float gradient_mul, const float *base18, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dense layers, fp32 (CUDA cores) - the parity arithmetic of the backbone / FPN / head

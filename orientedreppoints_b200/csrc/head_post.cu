@@ -184,6 +184,39 @@ gather_kernel(const int32_t *__restrict__ sorted_vals, const int32_t *__restrict
     }
 }
 
+// padded detections -> the all-gather payload [B, cap + 1, 28]: rows = 27 detection values | label, zero padded; row `cap`
+// carries the image's count in column 0 (orientedreppoints_b200/gather.py layout) - one launch instead of a fill + 3 copies
+__global__ void __launch_bounds__(256)
+pack_kernel(const float *__restrict__ dets, const int64_t *__restrict__ labels, const int32_t *__restrict__ counts, int B, int cap,
+            float *__restrict__ out)
+{
+    const size_t total = (size_t)B * (cap + 1) * 28;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int col = (int)(i % 28);
+        const size_t row = i / 28;
+        const int r = (int)(row % (cap + 1)), b = (int)(row / (cap + 1));
+        float v = 0.f;
+        if (r < cap) v = col < 27 ? dets[((size_t)b * cap + r) * 27 + col] : (float)labels[(size_t)b * cap + r];
+        else if (col == 0) v = (float)counts[b];
+        out[i] = v;
+    }
+}
+
+// head :162-163 for all levels at once:  offset = (1 - g) * pts + g * pts - base[c]  (fp32, evaluated as written there)
+struct OffsetProb { const float *pts; float *off; long long n; };
+struct OffsetParams { OffsetProb p[8]; int nprob; float g; float base[18]; };
+__global__ void __launch_bounds__(256)
+dcn_offsets_kernel(const __grid_constant__ OffsetParams P)
+{
+    const OffsetProb &pr = P.p[blockIdx.y];
+    const float g = P.g, og = 1.f - P.g;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pr.n; i += (long long)gridDim.x * blockDim.x) {
+        const float t = pr.pts[i];
+        // no FMA contraction: the reference evaluates two products, a sum and a difference, each rounded
+        pr.off[i] = __fsub_rn(__fadd_rn(__fmul_rn(og, t), __fmul_rn(g, t)), P.base[(int)(i % 18)]);
+    }
+}
+
 int grid_for(size_t items, int threads)
 {
     size_t g = (items + threads - 1) / threads;
@@ -273,6 +306,41 @@ extern "C" int orp_head_postprocess(int nlevels, const float *const *cls, const 
     count_launches((sel_bits + 7) / 8 + 1);
     gather_kernel<<<dim3(ceil_div(max_per_img, 128), B), 128, 0, st>>>(sv2, counts, O.dets, O.rp, O.box, (int)per_img, S,
                                                                      num_cls, max_per_img, B, dets_out, labels_out, counts_out, nms_ovf);
+    ORP_LAUNCHED();
+    return ORP_OK;
+}
+
+extern "C" int orp_pack_detections(const float *dets, const int64_t *labels, const int32_t *counts, int B, int max_per_img,
+                                   float *packed_out, void *stream)
+{
+    if (!dets || !labels || !counts || !packed_out || B < 1 || max_per_img < 1) return fail(ORP_EINVAL, "orp_pack_detections: bad arguments");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const size_t total = (size_t)B * (max_per_img + 1) * 28;
+    pack_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dets, labels, counts, B, max_per_img, packed_out);
+    ORP_LAUNCHED();
+    return ORP_OK;
+}
+
+extern "C" int orp_dcn_offsets_multi(int nprob, const float *const *pts, float *const *off, const long long *numel,
+                                     float gradient_mul, const float *base18, void *stream)
+{
+    if (nprob < 1 || nprob > 8 || !pts || !off || !numel || !base18) return fail(ORP_EINVAL, "orp_dcn_offsets_multi: bad arguments");
+    int rc = ensure_device();
+    if (rc) return rc;
+    OffsetParams P;
+    memset(&P, 0, sizeof(P));
+    P.nprob = nprob; P.g = gradient_mul;
+    long long mx = 0;
+    for (int i = 0; i < nprob; ++i) {
+        if (!pts[i] || !off[i] || numel[i] < 0 || numel[i] % 18) return fail(ORP_EINVAL, "orp_dcn_offsets_multi: bad problem");
+        P.p[i].pts = pts[i]; P.p[i].off = off[i]; P.p[i].n = numel[i];
+        mx = numel[i] > mx ? numel[i] : mx;
+    }
+    for (int c = 0; c < 18; ++c) P.base[c] = base18[c];
+    if (mx == 0) return ORP_OK;
+    dim3 grid((unsigned)grid_for((size_t)mx, 256), (unsigned)nprob);
+    dcn_offsets_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(P);
     ORP_LAUNCHED();
     return ORP_OK;
 }

@@ -143,6 +143,8 @@ class OrientedRepPointsDetector:
         base = np.arange(-1, 2).astype(np.float64)
         off = np.stack([np.repeat(base, 3), np.tile(base, 3)], axis=1).reshape(-1)        # head :78-88 (dy,dx)
         self.dcn_base_offset = torch.tensor(off, dtype=torch.float32, device=self.device).view(1, 1, 1, 18)
+        import ctypes
+        self._dcn_base_host = (ctypes.c_float * 18)(*[float(v) for v in off])
 
     # ------------------------------------------------------------------ weights
     def _load(self, sd):
@@ -261,8 +263,15 @@ class OrientedRepPointsDetector:
             cf = e.conv_gn_multi(cf, lc, nc, relu=True)
             pf = e.conv_gn_multi(pf, lr, nr, relu=True)
         init = e.conv_multi(e.conv_multi(pf, self.init_conv, relu=True), self.init_out, out_f32=True)   # [N,H,W,18]
-        # head :162-163, evaluated in fp32 exactly as written there
-        offsets = [(((1 - gradient_mul) * t + gradient_mul * t) - self.dcn_base_offset).contiguous() for t in init]
+        # head :162-163, evaluated in fp32 exactly as written there - one launch for the five levels
+        import ctypes
+        offsets = [torch.empty_like(t) for t in init]
+        n = len(init)
+        pa = (ctypes.c_void_p * n)(*[t.data_ptr() for t in init])
+        po = (ctypes.c_void_p * n)(*[t.data_ptr() for t in offsets])
+        ne = (ctypes.c_longlong * n)(*[t.numel() for t in init])
+        _lib.check(_lib.lib().orp_dcn_offsets_multi(n, pa, po, ne, float(gradient_mul), self._dcn_base_host, _lib.current_stream_ptr()),
+                   "orp_dcn_offsets_multi")
         cls = e.conv_multi(e.deform_conv_multi(cf, offsets, self.cls_dcn, relu=True), self.cls_out, out_f32=True)
         ref = e.conv_multi(e.deform_conv_multi(pf, offsets, self.ref_dcn, relu=True), self.ref_out, out_f32=True,
                            residual_f32=init)

@@ -15,6 +15,15 @@ def pack(dets, labels, counts):
     """padded (dets [T,cap,27], labels [T,cap], counts [T]) -> (buf [T,cap+1,28], counts): rows 0..cap-1 are the detections,
     row `cap` carries the tile's count in column 0 (exact in fp32 up to 2^24), so payload and counts travel in ONE collective"""
     t, cap = dets.shape[0], dets.shape[1]
+    if dets.is_cuda and dets.dtype == torch.float32:
+        # one kernel of the library instead of a fill and three strided copies
+        from . import _lib
+        buf = torch.empty((t, cap + 1, 28), dtype=torch.float32, device=dets.device)
+        d, l, c = dets.contiguous(), labels.to(torch.int64).contiguous(), counts.to(torch.int32).contiguous()
+        with torch.cuda.device(dets.device):
+            _lib.check(_lib.lib().orp_pack_detections(_lib.ptr(d), _lib.ptr(l), _lib.ptr(c), t, cap, _lib.ptr(buf),
+                                                      _lib.current_stream_ptr()), "orp_pack_detections")
+        return buf, c
     buf = torch.zeros((t, cap + 1, 28), dtype=dets.dtype, device=dets.device)
     buf[:, :cap, :27] = dets
     buf[:, :cap, 27] = labels.to(dets.dtype)

@@ -6,6 +6,10 @@ difference, documented in DESIGN.md: the reference makes NMS class-aware by addi
 every coordinate (:156-158) and running its fp32 rnms there, which is numerically unstable (511
 vs 660 survivors on the 1k fixture at +16000).  Here the label is passed to the NMS kernel as the segment
 id - the exact meaning of the offset trick - and coordinates are left untouched.
+
+`nms_cfg = dict(type='rnms', iou_thr=..., mode='compat32')` switches to the reference's literal behaviour for
+bit-for-bit reproduction runs: coordinates offset by label * (max + 1) exactly as :156-158 and the fp32 IoU arithmetic of
+rnms_kernel.cu (ORP_NMS_COMPAT32), no segments.
 """
 import torch
 
@@ -40,7 +44,13 @@ def multiclass_rnms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, 
     nms_cfg_ = nms_cfg.copy()
     nms_type = nms_cfg_.pop('type', 'rnms')
     nms_op = getattr(nms_wrapper, nms_type)
-    dets, keep = nms_op(torch.cat([bboxes, scores[:, None]], 1), segments=labels, **nms_cfg_)
+    if nms_cfg_.get('mode') == 'compat32':
+        # the reference, literally: class-aware through coordinate offsets, fp32 IoU (bbox_nms.py:156-164)
+        max_coordinate = bboxes.max()
+        offsets = labels.to(bboxes) * (max_coordinate + 1)
+        dets, keep = nms_op(torch.cat([bboxes + offsets[:, None], scores[:, None]], 1), **nms_cfg_)
+    else:
+        dets, keep = nms_op(torch.cat([bboxes, scores[:, None]], 1), segments=labels, **nms_cfg_)
     bboxes = bboxes[keep]
     if multi_reppoints is not None:
         reppoints = reppoints[keep]

@@ -55,6 +55,17 @@ def get_bboxes_single(cls_scores, points_preds, strides, scale_factor, cfg, resc
     return mlvl_bboxes, mlvl_scores
 
 
+def scalar_scale_factor(sf):
+    """img_meta['scale_factor'] as one number.  mmdet's Resize writes a float with keep_ratio=True (every config of this path)
+    and a 4-vector (w, h, w, h) otherwise; the head divides its 8 box / 18 point coordinates by it (:766-768), which only
+    broadcasts for a scalar - a vector is accepted here when all its entries agree"""
+    import numpy as np
+    a = np.asarray(sf, dtype=np.float64).reshape(-1)
+    if a.size == 0 or not np.all(a == a[0]):
+        raise ValueError("scale_factor %r: the rotated-box head needs one scale for x and y (keep_ratio=True)" % (sf,))
+    return float(a[0])
+
+
 def get_bboxes_fused(cls_scores, pts_preds_refine, strides, img_metas, cfg, rescale=False):
     """The same computation as get_bboxes() as ONE device-resident pipeline (orp_head_postprocess): returns
     padded (dets [B,max_per_img,27], labels [B,max_per_img], counts [B]) device tensors, no host sync."""
@@ -77,9 +88,10 @@ def get_bboxes_fused(cls_scores, pts_preds_refine, strides, img_metas, cfg, resc
     counts = torch.empty((b,), dtype=torch.int32, device=dev)
     sf = None
     if rescale:
-        sf = torch.tensor([float(m['scale_factor']) for m in img_metas], dtype=torch.float32).to(dev, non_blocking=True)
+        sf = torch.tensor([scalar_scale_factor(m['scale_factor']) for m in img_metas], dtype=torch.float32).to(dev, non_blocking=True)
     nms_cfg = cfg['nms']
-    assert nms_cfg.get('type', 'rnms') == 'rnms'
+    if nms_cfg.get('type', 'rnms') != 'rnms' or nms_cfg.get('mode', 'exact64') != 'exact64':
+        raise ValueError("get_bboxes_fused serves nms type 'rnms' in the default arithmetic; use get_bboxes() for %r" % (nms_cfg,))
     with torch.cuda.device(dev):
         rc = _lib.lib().orp_head_postprocess(n, pa, pr, hs, ws, ss, b, cls_c[0].shape[3], int(cfg.get('nms_pre', -1)),
                                              float(cfg['score_thr']), float(nms_cfg['iou_thr']), cap, _lib.ptr(sf),

@@ -313,7 +313,7 @@ class OrientedRepPointsDetector:
         return self._g_out
 
     # ------------------------------------------------------------------ simple_test
-    def simple_test(self, img, img_metas=None, rescale=True, return_tensors=False):
+    def simple_test(self, img, img_metas=None, rescale=False, return_tensors=False):
         with torch.cuda.device(self.device):
             return self._simple_test(img, img_metas, rescale, return_tensors)
 
@@ -326,13 +326,16 @@ class OrientedRepPointsDetector:
         n = img.shape[0]
         if img_metas is None:
             img_metas = [dict(scale_factor=1.0) for _ in range(n)]
-        if getattr(self, "fused_post", True):
+        nms_cfg = self.test_cfg['nms']
+        if getattr(self, "fused_post", True) and nms_cfg.get('type', 'rnms') == 'rnms' and nms_cfg.get('mode', 'exact64') == 'exact64':
             from .core.get_bboxes import get_bboxes_fused
             dets, labels, counts = get_bboxes_fused([o[0] for o in outs], [o[2] for o in outs], STRIDES, img_metas,
                                                     self.test_cfg, rescale)
             if return_tensors == "padded":
                 return dets, labels, counts
             cnt = counts.tolist()                                      # the one host sync of a step
+            if any(c < 0 for c in cnt):
+                raise _lib.OrpError("rotated NMS candidate list overflowed its buffer (orp_head_postprocess): results invalid")
             results = [(dets[i, :cnt[i]], labels[i, :cnt[i]]) for i in range(n)]
         else:
             results = get_bboxes([o[0] for o in outs], [o[2] for o in outs], STRIDES, img_metas, self.test_cfg, rescale)

@@ -7,7 +7,8 @@ tools/parse_pkl/parse_pkl_mege_results_for_dota_evaluation.py:93-192.
 Semantics kept: suppression predicate `iou <= thresh` keeps (a NaN IoU suppresses), selection in score
 order, output order = first appearance of each original image, then kept detections in score order,
 `imgname confidence x1 y1 ... x4 y4` with python float formatting.  Contract difference: the GPU kernel
-consumes float32 coordinates (like the reference's own poly_gpu_nms); text output keeps the doubles.
+consumes float32 coordinates (like the reference's own poly_gpu_nms) - of boxes translated, in float64, to their image's own
+origin, so the cast costs ~1e-5 px instead of ~1e-3 px at full-image coordinates; text output keeps the doubles.
 """
 import os
 import re
@@ -26,6 +27,20 @@ _PAT_RATE = re.compile(r'__([\d+\.]+)__\d+___')
 
 def _nms_segmented(dets, thresh, segments=None, device=None):
     dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    dets = np.asarray(dets)
+    if dets.dtype == np.float64 and dets.shape[0]:
+        # full-image coordinates (10^4 px) lose ~1e-3 px in a float32 cast.  IoU is translation invariant, so every segment
+        # (original image) is moved to its own origin in float64 first: the float32 the kernel consumes then carries the
+        # reference's doubles to ~1e-5 px instead
+        seg_ids = np.zeros(dets.shape[0], np.int64) if segments is None else np.asarray(segments, np.int64)
+        nseg = int(seg_ids.max()) + 1
+        ox = np.full(nseg, np.inf)
+        oy = np.full(nseg, np.inf)
+        np.minimum.at(ox, seg_ids, dets[:, 0:8:2].min(axis=1))
+        np.minimum.at(oy, seg_ids, dets[:, 1:8:2].min(axis=1))
+        dets = dets.copy()
+        dets[:, 0:8:2] -= np.floor(ox[seg_ids])[:, None]
+        dets[:, 1:8:2] -= np.floor(oy[seg_ids])[:, None]
     d = torch.from_numpy(np.ascontiguousarray(dets, dtype=np.float32)).to(dev)
     seg = None if segments is None else torch.from_numpy(np.ascontiguousarray(segments, dtype=np.int32)).to(dev)
     keep = rnms_indices(d, float(thresh), segments=seg, mode="exact64", union_mode=_lib.ORP_UNION_NAN_SUPPRESSES,

@@ -7,9 +7,9 @@ from .convex_iou import convex_giou, convex_iou, convex_overlaps
 from .dcn import (DeformConv, DeformConvPack, ModulatedDeformConv, ModulatedDeformConvPack, deform_conv,
                   modulated_deform_conv)
 from .minarea_rect import minaerarect
-from .nms_wrapper import rnms, rnms_indices
+from .nms_wrapper import rnms, rnms_indices, soft_rnms
 from .norm import build_norm_layer
 
-__all__ = ['rnms', 'rnms_indices', 'minaerarect', 'box_iou_rotated', 'quad_iou_matrix', 'convex_iou', 'convex_overlaps',
+__all__ = ['rnms', 'rnms_indices', 'soft_rnms', 'minaerarect', 'box_iou_rotated', 'quad_iou_matrix', 'convex_iou', 'convex_overlaps',
            'convex_giou', 'DeformConv', 'DeformConvPack', 'ModulatedDeformConv', 'ModulatedDeformConvPack', 'deform_conv',
            'modulated_deform_conv', 'ConvModule', 'build_conv_layer', 'build_norm_layer']

@@ -11,6 +11,8 @@ def convex_iou(pred, target):
     if not (torch.is_tensor(pred) and pred.is_cuda and torch.is_tensor(target) and target.is_cuda):
         raise TypeError('ex_boxes must be a CUDA tensor')          # convex_iou_kernel.cu:317-318 AT_ASSERTM
     ex_num, gt_num = pred.size(0), target.size(0)
+    if ex_num == 0 or gt_num == 0:
+        return pred.new_zeros((ex_num, gt_num), dtype=torch.float32)
     p = pred.detach().float().contiguous().reshape(ex_num, 18)
     t = target.detach().float().contiguous().reshape(gt_num, 8)
     out = torch.empty((ex_num, gt_num), dtype=torch.float32, device=pred.device)

@@ -268,3 +268,28 @@ def test_convex_iou_matches_oracle_bit_exact(cuda, po):
     with pytest.raises(TypeError):
         convex_iou(torch.zeros(1, 18), torch.zeros(1, 8))
     assert convex_iou(torch.zeros(0, 18, device=cuda), torch.from_numpy(quads).to(cuda)).shape == (0, k)
+
+
+def test_soft_rnms_equals_reference(cuda, golden):
+    """soft_rnms (nms_wrapper.py:120-175 / rnms_cpu.cpp:165-320) against vectors minted by the reference's own compiled
+    soft_rnms (tests/golden/gen_golden_soft_rnms.py): kept set, ORDER and decayed scores, for the three methods"""
+    from orientedreppoints_b200.ops import soft_rnms
+    g = golden("soft_rnms.npz")
+    for name in ("rand600", "clustered"):
+        d = g[name + "_dets"]
+        for method in ("original", "linear", "gaussian"):
+            for thr in (0.3, 0.5):
+                ref = g["%s_%s_thr%02d" % (name, method, int(thr * 10))]
+                new_dets, inds = soft_rnms(d, thr, method=method, sigma=0.5, min_score=1e-3)
+                assert new_dets.dtype == d.dtype and inds.dtype == np.int64
+                assert np.array_equal(inds, ref[:, 9].astype(np.int64)), (name, method, thr)
+                assert np.array_equal(new_dets[:, :8], ref[:, :8])
+                if method == "gaussian":                       # expf of libm vs numpy: last-bit differences allowed
+                    assert np.allclose(new_dets[:, 8], ref[:, 8], rtol=2e-6, atol=0)
+                else:
+                    assert np.array_equal(new_dets[:, 8], ref[:, 8])
+    t = torch.from_numpy(g["rand600_dets"]).to(cuda)
+    nd, ind = soft_rnms(t, 0.3, method="linear")
+    assert nd.is_cuda and ind.dtype == torch.long and np.array_equal(ind.cpu().numpy(), g["rand600_linear_thr03"][:, 9].astype(np.int64))
+    with pytest.raises(ValueError):
+        soft_rnms(g["rand600_dets"], 0.3, method="nope")

@@ -285,6 +285,16 @@ int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const void *w, int C
 int orp_conv2d_f16x3(int nprob, const orp_tc_problem *probs, const void *w_split, int Cout, int Cout_padded,
                      int KH, int KW, int Cin, int stride, int pad, const float *bias, int wscale_log2, int relu,
                      int out_f32, int deform, void *stream);
+/* Split-K form of one plain convolution (no residual / deformation) for launches whose 128 x BN tiling leaves most SMs idle
+ * (P6: 3x3/2 over 2048 channels on a 16^2 map; layer4 and layer3 at one tile per step): the KH*KW taps are divided into
+ * `ksplit` groups (KH*KW % ksplit == 0), every (tile, group) is a CTA-sized unit of the same tcgen05 kernel writing its partial
+ * sums to its own slab of `workspace` (fp32 [ksplit, N,Ho,Wo,Cout]), and a finishing pass adds the slabs in a fixed order
+ * (bit-reproducible), applies bias / ReLU and writes
+ * bf16 (f16x3 == 0) or split fp16 (f16x3 != 0) to prob->out (+ GroupNorm statistics when prob->gn_stats is set).  Shorter
+ * accumulation chains also cut the tensor core's accumulator-truncation loss of the K = 18432 layer. */
+int orp_conv2d_tc_splitk(const orp_tc_problem *prob, const void *w, int Cout, int Cout_padded, int KH, int KW, int Cin,
+                         int stride, int pad, const float *bias, int f16x3, int wscale_log2, int relu, int ksplit,
+                         float *workspace, void *stream);
 /* number of tile rows that saturated since the last reset (host-blocking read of a device counter) */
 int orp_f16x3_overflow_count(unsigned int *count, int reset);
 /* stem in split form: space-to-depth planes fp16 [2][N, H/2+3, W/2+3, 16] (hi plane, lo plane) from the uint8 HWC

@@ -94,6 +94,9 @@ struct alignas(64) TcParams {
     int tma_epi, epi_bufs;                    // TMA epilogue on/off; output staging buffers (1 or 2)
     int epi_merge;                            // split mode, memory-bound layers: hi and lo tiles of a 64-column group leave in ONE pass
     int ncat;                                 // split mode, BN <= 128: terms concatenated along N (see the kernel header)
+    int ksplit;                               // split-K over the taps (launches with fewer tiles than SMs): partial sums meet in an fp32 buffer
+    FastDiv fd_ks;                            // / ksplit
+    long long ks_stride;                      // elements between the partial-sum slabs of consecutive K splits
     int b_resident;                           // short-K layers: the whole weight slab of this CTA's N tile stays in shared memory
     int res_mma;                              // residual added by the tensor core: extra K blocks  R[128x64] * I[64x64]
     int epi_split;                            // epilogue-bound layers: the two epilogue warpgroups work on alternate tiles (one per accumulator buffer)
@@ -269,22 +272,35 @@ struct Ring {
 //                             times smaller too, so the loss of a tile is that of K/16 steps instead of 3K/16.
 //   split, deformable:        (tap, channel block, term): the producers sample once and fill three stages back to back.
 struct KIter {
-    int tap = 0, term, cb = 0, phase = 0;
-    int taps, cbn, mode;                                   // mode 0: bf16, 1: split TMA, 2: split deformable
-    __device__ KIter(int taps_, int cbn_, int mode_) : taps(taps_), cbn(cbn_), mode(mode_) { term = (mode == 1) ? 1 : 0; }
+    int tap, term, cb = 0, phase = 0;
+    int tap0, taps, cbn, mode;                             // taps [tap0, taps); mode 0: bf16, 1: split TMA, 2: split deformable
+    __device__ KIter(int taps_, int cbn_, int mode_, int tap0_ = 0) : tap0(tap0_), taps(taps_), cbn(cbn_), mode(mode_)
+    {
+        tap = tap0;
+        term = (mode == 1) ? 1 : 0;
+    }
     __device__ void next()
     {
         if (mode == 0) { if (++cb == cbn) { cb = 0; ++tap; } }
         else if (mode == 2) { if (++term == 3) { term = 0; if (++cb == cbn) { cb = 0; ++tap; } } }
         else if (phase == 0) {
-            if (++cb == cbn) { cb = 0; if (++term == 3) { term = 1; if (++tap == taps) { tap = 0; term = 0; phase = 1; } } }
+            if (++cb == cbn) { cb = 0; if (++term == 3) { term = 1; if (++tap == taps) { tap = tap0; term = 0; phase = 1; } } }
         } else { if (++cb == cbn) { cb = 0; ++tap; } }
     }
 };
 
+__device__ __forceinline__ int ksplit_of(const TcParams &P, int tile)
+{
+    if (P.ksplit <= 1) return 0;
+    uint32_t q, r;
+    P.fd_ks.divmod((uint32_t)tile, q, r);
+    return (int)r;
+}
+
 __device__ __forceinline__ void decode_tile(const TcParams &P, int tile, int &pi, int &wb, int &hb, int &ib, int &nt)
 {
     uint32_t mt_u, nt_u;
+    if (P.ksplit > 1) tile = (int)P.fd_ks.div((uint32_t)tile);          // tile = (m tile, n tile, k split), k split fastest
     P.fd_ntn.divmod((uint32_t)tile, mt_u, nt_u);
     nt = (int)nt_u;
     const int mt = (int)mt_u;
@@ -388,7 +404,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int kblocks = P.KH * P.KW * P.cin_blocks * ((P.split && !P.ncat) ? 3 : 1);   // main-loop K blocks (stages) per tile
+    const int taps_per = (P.KH * P.KW) / (P.ksplit > 1 ? P.ksplit : 1);              // taps of one K split
+    const int kblocks = taps_per * P.cin_blocks * ((P.split && !P.ncat) ? 3 : 1);     // main-loop K blocks (stages) per tile
     // Programmatic dependent launch: the next kernel in the stream may start its CTAs (barrier init, TMEM allocation,
     // descriptor prefetch - the code above) on SMs this grid has already left; nothing above touches global memory,
     // and everything below (loads AND stores) comes after the wait for the preceding grid to complete and flush.
@@ -414,7 +431,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 decode_tile(P, tile, pi, wb, hb, ib, nt);
                 const Problem &pr = P.prob[pi];
                 const int w0 = wb * pr.BW * P.stride - P.pad, h0 = hb * pr.BH * P.stride - P.pad, i0 = ib * pr.BI;
-                KIter it(P.KH * P.KW, P.cin_blocks, (P.split && !P.ncat) ? (DEFORM ? 2 : 1) : 0);
+                const int tap_lo = ksplit_of(P, tile) * taps_per;
+                KIter it(tap_lo + taps_per, P.cin_blocks, (P.split && !P.ncat) ? (DEFORM ? 2 : 1) : 0, tap_lo);
                 for (int j = 0; j < kblocks; ++j, it.next()) {
                     const int kh = it.tap / P.KW, kw = it.tap - kh * P.KW;
                     mbar_wait(&empty[r.stage], r.phase ^ 1);
@@ -473,7 +491,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
             tcgen05_fence_after();
             const uint32_t accw = P.ncat ? 2u * BN : (uint32_t)BN;          // TMEM columns of one accumulator buffer
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * accw;
-            KIter it(P.KH * P.KW, P.cin_blocks, (P.split && !P.ncat) ? (DEFORM ? 2 : 1) : 0);   // same walk as the producer
+            const int tap_lo = ksplit_of(P, tile) * taps_per;
+            KIter it(tap_lo + taps_per, P.cin_blocks, (P.split && !P.ncat) ? (DEFORM ? 2 : 1) : 0, tap_lo);   // same walk as the producer
             for (int kb = 0; kb < kblocks; ++kb, it.next()) {
                 mbar_wait(&full[r.stage], r.phase);
                 tcgen05_fence_after();
@@ -566,6 +585,16 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                     if (valid && c0 < P.Cout) {
                         float *op = reinterpret_cast<float *>(pr.out) + pix * P.Cout + c0;
                         const float *rp = pr.res32 ? pr.res32 + pix * P.Cout + c0 : nullptr;
+                        if (P.ksplit > 1) {
+                            // split-K: this tile holds the sum over its taps only and writes it to its own slab of the fp32
+                            // workspace; the finishing kernel adds the slabs in a fixed order (bit-reproducible, unlike atomics)
+                            // and applies bias / activation / the hi-lo split
+                            float *sp = op + (long long)ksplit_of(P, tile) * P.ks_stride;
+                            for (int j = 0; j < 32; ++j) {
+                                if (c0 + j >= P.Cout) break;
+                                sp[j] = __uint_as_float(v[j]) * P.oscale;
+                            }
+                        } else
                         for (int j = 0; j < 32; ++j) {
                             if (c0 + j >= P.Cout) break;
                             float f = __uint_as_float(v[j]) * P.oscale;
@@ -1179,7 +1208,7 @@ extern "C" int orp_tc_timing_collect(float *total_ms, int *launches, double *flo
 
 static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *w, int Cout, int Cout_padded, int KH,
                             int KW, int Cin, int stride, int pad, const float *bias, int relu, int out_f32,
-                            int deform, int stem, void *stream, int split = 0, int wscale_log2 = 0);
+                            int deform, int stem, void *stream, int split = 0, int wscale_log2 = 0, int ksplit = 1);
 
 /* see include/orp_b200.h */
 extern "C" int orp_conv2d_bf16(int nprob, const orp_tc_problem *probs, const void *w, int Cout, int Cout_padded, int KH,
@@ -1248,15 +1277,103 @@ extern "C" int orp_stem_conv_s2d_bf16(const void *x_s2d, int N, int H, int W, co
     return conv2d_bf16_impl(1, &q, w256, 64, 64, 4, 1, 64, 1, 0, bias, relu, 0, 0, 2, stream);
 }
 
+namespace orp {
+namespace {
+// split-K finish: fp32 sums [pixels, C] -> + bias -> ReLU -> bf16 [pixels, C] or split fp16 [pixels, 2, C]
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const float *__restrict__ ws, int ksplit, size_t pixels, int C, const float *__restrict__ bias, int relu, int split,
+                     void *__restrict__ out, unsigned int *ovf)
+{
+    const int c8 = C / 8;
+    const size_t total = pixels * c8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pix = i / c8;
+        const int c = (int)(i - pix * c8) * 8;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < ksplit; ++k) {                       // fixed order: the sum is reproducible bit for bit
+            const float *p = ws + (size_t)k * pixels * C + pix * C + c;
+            const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+        float amax = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (bias) v[j] += bias[c + j];
+            if (relu) v[j] = fmaxf(v[j], 0.f);
+            amax = fmaxf(amax, fabsf(v[j]));
+        }
+        uint32_t hi[4], lo[4];
+        if (split) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const __half2 h2 = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+                const float2 hf = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(v[2 * k] - hf.x, v[2 * k + 1] - hf.y);
+                hi[k] = *reinterpret_cast<const uint32_t *>(&h2);
+                lo[k] = *reinterpret_cast<const uint32_t *>(&l2);
+            }
+            __half *o = static_cast<__half *>(out) + pix * 2 * C + c;
+            *reinterpret_cast<uint4 *>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(o + C) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            if (amax > 65504.f) atomicAdd(ovf, 1u);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+                hi[k] = *reinterpret_cast<uint32_t *>(&b2);
+            }
+            *reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(out) + pix * C + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        }
+    }
+}
+}  // namespace
+}  // namespace orp
+
+/* see include/orp_b200.h */
+extern "C" int orp_conv2d_tc_splitk(const orp_tc_problem *prob, const void *w, int Cout, int Cout_padded, int KH, int KW, int Cin,
+                                    int stride, int pad, const float *bias, int f16x3, int wscale_log2, int relu, int ksplit,
+                                    float *workspace, void *stream)
+{
+    if (!prob || !w || !workspace || ksplit < 2 || (Cout % 8)) return fail(ORP_EINVAL, "conv2d_tc_splitk: bad arguments");
+    if (f16x3 && (wscale_log2 < 0 || wscale_log2 > 15)) return fail(ORP_EINVAL, "conv2d_tc_splitk: weight scale exponent must be in 0..15");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int Ho = (prob->H + 2 * pad - (KH - 1) - 1) / stride + 1, Wo = (prob->W + 2 * pad - (KW - 1) - 1) / stride + 1;
+    if (Ho <= 0 || Wo <= 0) return fail(ORP_EINVAL, "conv2d_tc_splitk: bad problem");
+    const size_t pixels = (size_t)prob->N * Ho * Wo;
+    orp_tc_problem q = *prob;                                  // every (pixel, channel, split) element of the workspace is written
+    q.out = workspace;
+    q.gn_stats = nullptr;
+    int rc = conv2d_bf16_impl(1, &q, w, Cout, Cout_padded, KH, KW, Cin, stride, pad, nullptr, 0, 1, 0, 0, stream, f16x3 ? 1 : 0,
+                              wscale_log2, ksplit);
+    if (rc) return rc;
+    void *ovf = nullptr;
+    ORP_CUDA(cudaGetSymbolAddress(&ovf, g_f16_overflow));
+    const size_t items = pixels * (Cout / 8);
+    size_t g = (items + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    splitk_finish_kernel<<<(unsigned)(g ? g : 1), 256, 0, st>>>(workspace, ksplit, pixels, Cout, bias, relu, f16x3 ? 1 : 0, prob->out,
+                                                                static_cast<unsigned int *>(ovf));
+    ORP_LAUNCHED();
+    if (prob->gn_stats) {
+        if (Cout != 256) return fail(ORP_EINVAL, "conv2d_tc_splitk: gn_stats needs 256 output channels");
+        return f16x3 ? orp_gn_stats_f16x3(prob->out, prob->N, Ho * Wo, 256, 32, prob->gn_stats, stream)
+                     : orp_gn_stats_bf16(prob->out, prob->N, Ho * Wo, 256, 32, prob->gn_stats, stream);
+    }
+    return ORP_OK;
+}
+
 static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *w, int Cout, int Cout_padded, int KH,
                             int KW, int Cin, int stride, int pad, const float *bias, int relu, int out_f32,
-                            int deform, int stem, void *stream, int split, int wscale_log2)
+                            int deform, int stem, void *stream, int split, int wscale_log2, int ksplit)
 {
     if (nprob < 1 || nprob > kMaxProb || !probs || !w) return fail(ORP_EINVAL, "conv2d_tc: bad arguments");
     if (Cin % 8) return fail(ORP_EINVAL, "conv2d_tc: Cin must be a multiple of 8 (16-byte channel rows)");
     if (deform && !stem && (Cin % kBK)) return fail(ORP_EINVAL, "conv2d_tc: deformable conv needs Cin % 64 == 0");
     if (Cout_padded % 32 || Cout_padded < Cout) return fail(ORP_EINVAL, "conv2d_tc: padded Cout must be a multiple of 32");
     if (split && stem == 1) return fail(ORP_EINVAL, "conv2d_tc: the direct stem has no f16x3 form (use the space-to-depth stem)");
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > 1 && (nprob != 1 || deform || stem || !out_f32 || (KH * KW) % ksplit || probs[0].residual_bf16 || probs[0].residual_f32 || bias || relu))
+        return fail(ORP_EINVAL, "conv2d_tc: split-K serves one plain problem with an fp32 partial-sum output and taps % ksplit == 0");
     int rc = ensure_device();
     if (rc) return rc;
     EncodeTiledFn enc = encode_fn();
@@ -1274,7 +1391,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
             const int ho = (probs[i].H + 2 * pad - (KH - 1) - 1) / stride + 1, wo = (probs[i].W + 2 * pad - (KW - 1) - 1) / stride + 1;
             mtiles += ((long long)probs[i].N * ho * wo + 127) / 128;
         }
-        while (BN > 64 && mtiles * (Cout_padded / BN) < 120) BN /= 2;
+        while (BN > 64 && mtiles * (Cout_padded / BN) * ksplit < 120) BN /= 2;
     }
     TcParams P;
     memset(&P, 0, sizeof(P));
@@ -1352,7 +1469,10 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
         if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_tc: cuTensorMapEncodeTiled(B) failed");
     }
     P.num_m_tiles = mt;
-    P.num_tiles = mt * P.n_tiles_n;
+    P.num_tiles = mt * P.n_tiles_n * ksplit;
+    P.ksplit = ksplit;
+    P.fd_ks.set((uint32_t)ksplit);
+    P.ks_stride = (long long)P.prob[0].N * P.prob[0].Ho * P.prob[0].Wo * Cout;
     // TMA epilogue: 16-bit outputs whose channel count is a multiple of 64
     bool any_res = false;
     for (int i = 0; i < nprob; ++i) any_res = any_res || (probs[i].residual_bf16 != nullptr);
@@ -1403,7 +1523,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
         if (r != CUDA_SUCCESS) return fail(ORP_ECUDA, "conv2d_tc: cuTensorMapEncodeTiled(identity) failed");
     }
     // layers whose whole weight slab for one N tile is <= 72 KiB keep it resident; stages then carry only the A tile
-    P.b_resident = (!deform && KH * KW * T * P.cin_blocks * BN * kBK * 2 <= 72 * 1024 && !getenv("ORP_TC_NO_BRES")) ? 1 : 0;
+    P.b_resident = (!deform && ksplit == 1 && KH * KW * T * P.cin_blocks * BN * kBK * 2 <= 72 * 1024 && !getenv("ORP_TC_NO_BRES")) ? 1 : 0;
     if (P.tma_epi) {
         for (int i = 0; i < nprob; ++i) {
             const Problem &pr = P.prob[i];

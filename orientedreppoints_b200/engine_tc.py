@@ -128,6 +128,27 @@ class EngineTC:
                                       _lib.ptr(bias), int(relu), int(out_f32), int(deform), _lib.current_stream_ptr())
         _lib.check(rc, "orp_conv2d_bf16")
 
+    @staticmethod
+    def _ksplit(n, ho, wo, L, nprob, relu, residual, out_f32, residual_f32):
+        """split-K factor for a launch whose tiling would leave most of the 148 SMs idle (3x3 layers on small maps)"""
+        if nprob != 1 or L.kh * L.kw != 9 or residual is not None or residual_f32 is not None or out_f32 or relu == 2 or L.cout % 8:
+            return 1
+        mt = -(-(n * ho * wo) // 128)
+        if mt * -(-L.cout // 64) > 74:           # the narrow-tile (BN = 64) launch already fills half the machine: measured faster
+            return 1                             # than split-K there (64^2 x 256 -> 256: 45 us vs 76 us)
+        tiles = mt * -(-L.cout // 256)
+        return 9 if tiles * 9 <= 2 * 148 else 3
+
+    def _conv_splitk(self, x, y, tc, L, relu, ks, stats, f16x3):
+        ws = torch.empty((ks, y.shape[0], y.shape[1], y.shape[2], L.cout), dtype=torch.float32, device=self.device)
+        q = _lib.TcProblem()
+        q.x, q.N, q.H, q.W, q.out = x.data_ptr(), x.shape[0], x.shape[1], x.shape[2], y.data_ptr()
+        q.gn_stats = stats.data_ptr() if stats is not None else None
+        rc = self.lib.orp_conv2d_tc_splitk(ctypes.byref(q), _lib.ptr(tc["w"]), L.cout, tc["cout_p"], L.kh, L.kw, L.w_raw.shape[3], L.stride,
+                                           L.pad, _lib.ptr(L.bias), int(f16x3), int(tc.get("s", 0)), int(bool(relu)), ks, _lib.ptr(ws),
+                                           _lib.current_stream_ptr())
+        _lib.check(rc, "orp_conv2d_tc_splitk")
+
     def conv_multi(self, xs, L, relu=False, residual=None, out_f32=False, residual_f32=None, stats=None):
         """relu: False/True, or 2 for the exact-GELU epilogue (Swin MLP); stats: per-problem double [N,32,2] tensors
         (zeroed) that receive the GroupNorm statistics of the outputs"""
@@ -140,6 +161,10 @@ class EngineTC:
             wo = (w + 2 * L.pad - L.kw) // L.stride + 1
             ys.append(torch.empty((n, ho, wo, L.cout), dtype=torch.float32 if out_f32 else torch.bfloat16,
                                   device=self.device))
+        ks = self._ksplit(ys[0].shape[0], ys[0].shape[1], ys[0].shape[2], L, len(xs), relu, residual, out_f32, residual_f32)
+        if ks > 1:
+            self._conv_splitk(xs[0], ys[0], tc, L, relu, ks, None if stats is None else stats[0], False)
+            return ys
         self._launch(xs, ys, tc, L.cout, L.kh, L.kw, L.w_raw.shape[3], L.stride, L.pad, L.bias, relu, out_f32, False,
                      res=residual, res32=residual_f32, stats=stats)
         return ys
@@ -345,6 +370,10 @@ class EngineTCSplit(EngineTC):
             wo = (w + 2 * L.pad - L.kw) // L.stride + 1
             ys.append(torch.empty((n, ho, wo, L.cout), dtype=torch.float32, device=self.device) if out_f32 else
                       torch.empty((n, ho, wo, 2, L.cout), dtype=torch.float16, device=self.device))
+        ks = self._ksplit(ys[0].shape[0], ys[0].shape[1], ys[0].shape[2], L, len(xs), relu, residual, out_f32, residual_f32)
+        if ks > 1:
+            self._conv_splitk(xs[0], ys[0], tc, L, relu, ks, None if stats is None else stats[0], True)
+            return ys
         self._launch(xs, ys, tc, L.cout, L.kh, L.kw, L.w_raw.shape[3], L.stride, L.pad, L.bias, relu, out_f32, False,
                      res=residual, res32=residual_f32, stats=stats)
         return ys

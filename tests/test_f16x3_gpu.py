@@ -218,3 +218,37 @@ def test_dense_graph_f16x3_1024_and_detections(cuda, depth):
     # random-init scores are near-ties (all ~0.01), so a 1e-5 difference re-orders a few candidates at the nms_pre cut
     assert frac > 0.98 and back > 0.98
     assert float((d[matched, 26] - rd[arg[matched], 26]).abs().max()) < 1e-4   # scores
+
+
+@pytest.mark.parametrize("mode", ["f16x3", "bf16"])
+def test_conv_splitk_small_maps(cuda, mode):
+    """launches with fewer tiles than SMs run split-K over the taps (partial sums through an fp32 buffer + finishing pass);
+    same results as the plain kernel, bias / ReLU / GroupNorm statistics included"""
+    import torch.nn.functional as F
+    from orientedreppoints_b200.detector import ConvLayer
+    from orientedreppoints_b200.engine_tc import EngineTC, EngineTCSplit
+    e = EngineTCSplit(cuda) if mode == "f16x3" else EngineTC(cuda)
+    g = torch.Generator().manual_seed(21)
+    for (cin, cout, s, h, w, n, want) in [(2048, 256, 2, 32, 32, 1, 9), (512, 512, 1, 32, 32, 1, 9), (256, 256, 2, 16, 16, 2, 9), (256, 256, 1, 32, 32, 2, 9), (256, 256, 1, 64, 64, 1, 1)]:
+        x = torch.randn(n, cin, h, w, generator=g)
+        wt = torch.randn(cout, cin, 3, 3, generator=g) * (1.0 / (cin * 9) ** 0.5)
+        b = torch.randn(cout, generator=g)
+        L = ConvLayer(wt, b, s, 1, cuda)
+        ho = (h + 2 - 3) // s + 1
+        assert e._ksplit(n, ho, ho, L, 1, True, None, False, None) == want
+        xin = x.bfloat16().float() if mode == "bf16" else x
+        # fp64 reference on the device (torch's CPU convolutions crawl on the GPU box's 128 host threads)
+        ref = F.relu(F.conv2d(xin.double().to(cuda), (wt.bfloat16().float() if mode == "bf16" else wt).double().to(cuda), b.double().to(cuda), s, 1))
+        y = e.conv(e.from_float(x.permute(0, 2, 3, 1).contiguous()), L, relu=True)
+        tol = 6e-3 if mode == "bf16" else OP_TOL
+        assert _rel(_nchw(e.to_float(y)), ref) < tol, (cin, cout, want)
+    if mode == "f16x3":
+        # GroupNorm statistics of a split-K layer (P6 of the FPN): the conv_gn path
+        from orientedreppoints_b200.detector import Norm
+        x = torch.randn(1, 512, 16, 16, generator=g)
+        wt = torch.randn(256, 512, 3, 3, generator=g) * 0.02
+        sd = {"n.weight": torch.rand(256, generator=g) + 0.5, "n.bias": torch.randn(256, generator=g) * 0.1}
+        ref = F.group_norm(F.conv2d(x.double().to(cuda), wt.double().to(cuda), None, 2, 1), 32, sd["n.weight"].double().to(cuda),
+                           sd["n.bias"].double().to(cuda), 1e-5)
+        y = e.conv_gn(e.from_float(x.permute(0, 2, 3, 1).contiguous()), ConvLayer(wt, None, 2, 1, cuda), Norm(sd, "n", cuda))
+        assert _rel(_nchw(e.to_float(y)), ref) < 1e-5

@@ -388,6 +388,14 @@ int orp_patch_embed_rows_bf16(const float *img_nchw, int B, int H, int W, void *
 int orp_patch_merge_gather_bf16(const void *x, int B, int H, int W, int C, void *y, void *stream);
 /* F.max_pool2d(x, 1, stride=2) (necks/fpn.py:163-165): [B,H,W,C] -> [B,ceil(H/2),ceil(W/2),C] */
 int orp_subsample2_bf16(const void *x, int B, int H, int W, int C, void *y, void *stream);
+/* the same five kernels on split fp16 tokens [.., 2, C] (f16x3 engine: Swin-T in the parity arithmetic) */
+int orp_layernorm_f16x3(const void *x, int B, int H, int W, int C, const float *gamma, const float *beta, float eps,
+                        int Hp, int Wp, void *y, void *stream);
+int orp_window_attention_f16x3(const void *qkv, int B, int H, int W, int Hp, int Wp, int C, int heads, int shift,
+                               const float *bias_table, float scale, void *out, void *stream);
+int orp_patch_embed_rows_f16x3(const float *img_nchw, int B, int H, int W, void *out, void *stream);
+int orp_patch_merge_gather_f16x3(const void *x, int B, int H, int W, int C, void *y, void *stream);
+int orp_subsample2_f16x3(const void *x, int B, int H, int W, int C, void *y, void *stream);
 
 #ifdef __cplusplus
 }

@@ -366,15 +366,20 @@ def run(args, rank, world, local, benchmod):
         torch.cuda.empty_cache()
     if extras and depth == 50:
         # BASELINE.json configs[3] and [4]: R-101 at 4 tiles/GPU (batch 32 over 8 GPUs), Swin-T + DCN head at 8 tiles/GPU
-        # (batch 64 over 8 GPUs; bf16 - the Swin blocks have no f16x3 form yet)
+        # (batch 64 over 8 GPUs) - both in the benchmarked arithmetic; Swin-T also in single-pass bf16 for reference
         cfgs = {}
         try:
             cfgs["r101_b4_per_gpu"], d2, _ = run_config("r101", precision, 4, args, rank, world, local, benchmod, flush)
             del d2
             torch.cuda.empty_cache()
-            cfgs["swin_tiny_b8_per_gpu"], d3, _ = run_config("swin_tiny", "bf16", 8, args, rank, world, local, benchmod, flush)
+            cfgs["swin_tiny_b8_per_gpu"], d3, _ = run_config("swin_tiny", precision, 8, args, rank, world, local, benchmod, flush)
             del d3
             torch.cuda.empty_cache()
+            if precision != "bf16":
+                cfgs["swin_tiny_b8_per_gpu_bf16"], d4, _ = run_config("swin_tiny", "bf16", 8, args, rank, world, local, benchmod, flush,
+                                                                      steps=3)
+                del d4
+                torch.cuda.empty_cache()
         except Exception as ex:                                   # never lose the headline line to an extra
             cfgs["error"] = repr(ex)
         line["configs"] = cfgs

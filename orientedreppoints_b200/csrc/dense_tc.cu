@@ -1476,9 +1476,10 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     // TMA epilogue: 16-bit outputs whose channel count is a multiple of 64
     bool any_res = false;
     for (int i = 0; i < nprob; ++i) any_res = any_res || (probs[i].residual_bf16 != nullptr);
-    P.tma_epi = (!out_f32 && (Cout % 64 == 0) && BN >= 64) ? 1 : 0;
+    // (f16x3 also takes channel counts that are only a multiple of 8 - Swin's 96 / 288: the TMA unit clips the last box)
+    P.tma_epi = (!out_f32 && ((Cout % 64 == 0) || (split && Cout % 8 == 0)) && BN >= 64) ? 1 : 0;
     if (getenv("ORP_TC_NO_TMA_EPI") && !split) P.tma_epi = 0;
-    if (split && !out_f32 && !P.tma_epi) return fail(ORP_EINVAL, "conv2d_f16x3: 16-bit outputs need Cout % 64 == 0");
+    if (split && !out_f32 && !P.tma_epi) return fail(ORP_EINVAL, "conv2d_f16x3: 16-bit outputs need Cout % 8 == 0 and weights padded to a multiple of 64 rows");
     if (split && out_f32 && any_res) return fail(ORP_EINVAL, "conv2d_f16x3: fp32 outputs take an fp32 residual only");
     // GroupNorm statistics: fused into the TMA epilogue when every warp's 32 rows lie in one image
     bool want_gn = false, gn_ok = (P.tma_epi != 0) && Cout == 256 && !bias && !relu;

@@ -7,30 +7,60 @@
 // the zero-padded window grid), the window attention itself (shift, relative-position bias and the -100 region mask
 // are index arithmetic - no roll / partition / reverse copies), the 4x4 patch gather, the 2x2 merge gather and the
 // stride-2 subsample that max_pool2d(kernel 1, stride 2) is (necks/fpn.py:163-165).
+//
+// Every kernel exists for both activation formats of the tensor-core engines: bf16 [.., C] and the f16x3 "split" format
+// fp16 [.., 2, C] (per token C hi values, then C lo values, x = hi + lo); the arithmetic in between is fp32 either way.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
 namespace orp {
 namespace {
 
+// token-wise element access: `tok` = token (pixel) index, C = channels per token
+template <bool SPLIT> struct Act;
+template <> struct Act<false> {
+    typedef __nv_bfloat16 T;
+    static __device__ __forceinline__ float ld(const T *b, long long tok, int C, int c) { return __bfloat162float(b[tok * C + c]); }
+    static __device__ __forceinline__ void st(T *b, long long tok, int C, int c, float v) { b[tok * C + c] = __float2bfloat16_rn(v); }
+    static constexpr int planes = 1;
+};
+template <> struct Act<true> {
+    typedef __half T;
+    static __device__ __forceinline__ float ld(const T *b, long long tok, int C, int c)
+    {
+        const T *p = b + tok * 2 * C + c;
+        return __half2float(p[0]) + __half2float(p[C]);
+    }
+    static __device__ __forceinline__ void st(T *b, long long tok, int C, int c, float v)
+    {
+        const float a = fminf(fmaxf(v, -65504.f), 65504.f);
+        const __half h = __float2half_rn(a);
+        T *p = b + tok * 2 * C + c;
+        p[0] = h;
+        p[C] = __float2half_rn(a - __half2float(h));
+    }
+    static constexpr int planes = 2;
+};
+
 // one warp per token; out may be a padded grid [B,Hp,Wp,C] (rows beyond H,W pre-zeroed by the caller)
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
-layernorm_bf16_kernel(const __nv_bfloat16 *__restrict__ x, int B, int H, int W, int C, const float *__restrict__ gamma,
-                      const float *__restrict__ beta, float eps, int Hp, int Wp, __nv_bfloat16 *__restrict__ y)
+layernorm_kernel(const typename Act<SPLIT>::T *__restrict__ x, int B, int H, int W, int C, const float *__restrict__ gamma,
+                 const float *__restrict__ beta, float eps, int Hp, int Wp, typename Act<SPLIT>::T *__restrict__ y)
 {
     const int lane = threadIdx.x & 31;
     const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long ntok = (long long)B * H * W;
     if (tok >= ntok) return;
-    const __nv_bfloat16 *px = x + tok * C;
     float v[96];                                   // C <= 3072
     const int per = (C + 31) / 32;
     float s = 0.f;
 #pragma unroll 4
     for (int i = 0; i < per; ++i) {
         const int c = lane + i * 32;
-        v[i] = c < C ? __bfloat162float(px[c]) : 0.f;
+        v[i] = c < C ? Act<SPLIT>::ld(x, tok, C, c) : 0.f;
         s += v[i];
     }
 #pragma unroll
@@ -48,11 +78,11 @@ layernorm_bf16_kernel(const __nv_bfloat16 *__restrict__ x, int B, int H, int W, 
     const float rstd = rsqrtf(q / (float)C + eps);
     const int b = (int)(tok / ((long long)H * W)), hw = (int)(tok - (long long)b * H * W);
     const int h = hw / W, w = hw - h * W;
-    __nv_bfloat16 *py = y + (((long long)b * Hp + h) * Wp + w) * C;
+    const long long otok = ((long long)b * Hp + h) * Wp + w;
 #pragma unroll 4
     for (int i = 0; i < per; ++i) {
         const int c = lane + i * 32;
-        if (c < C) py[c] = __float2bfloat16_rn((v[i] - mean) * rstd * gamma[c] + beta[c]);
+        if (c < C) Act<SPLIT>::st(y, otok, C, c, (v[i] - mean) * rstd * gamma[c] + beta[c]);
     }
 }
 
@@ -60,10 +90,11 @@ layernorm_bf16_kernel(const __nv_bfloat16 *__restrict__ x, int B, int H, int W, 
 // block = 64 threads = one (window, head); thread t < 49 owns query token t of the window.
 constexpr int kWin = 7, kTok = 49, kHd = 32;
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(64)
-window_attention_kernel(const __nv_bfloat16 *__restrict__ qkv, int B, int H, int W, int Hp, int Wp, int C, int heads,
+window_attention_kernel(const typename Act<SPLIT>::T *__restrict__ qkv, int B, int H, int W, int Hp, int Wp, int C, int heads,
                         int shift, const float *__restrict__ bias_table /* [169, heads] */, float scale,
-                        __nv_bfloat16 *__restrict__ out)
+                        typename Act<SPLIT>::T *__restrict__ out)
 {
     __shared__ float sk[kTok][kHd + 1], sv[kTok][kHd + 1];
     __shared__ int s_src[kTok], s_reg[kTok];
@@ -87,18 +118,14 @@ window_attention_kernel(const __nv_bfloat16 *__restrict__ qkv, int B, int H, int
     __syncthreads();
     for (int e = t; e < kTok * kHd; e += 64) {
         const int j = e / kHd, d = e - j * kHd;
-        const __nv_bfloat16 *p = qkv + (long long)s_src[j] * (3 * C) + head * kHd + d;
-        sk[j][d] = __bfloat162float(p[C]);
-        sv[j][d] = __bfloat162float(p[2 * C]);
+        sk[j][d] = Act<SPLIT>::ld(qkv, s_src[j], 3 * C, C + head * kHd + d);
+        sv[j][d] = Act<SPLIT>::ld(qkv, s_src[j], 3 * C, 2 * C + head * kHd + d);
     }
     __syncthreads();
     if (t >= kTok) return;
     float q[kHd];
-    {
-        const __nv_bfloat16 *p = qkv + (long long)s_src[t] * (3 * C) + head * kHd;
 #pragma unroll
-        for (int d = 0; d < kHd; ++d) q[d] = __bfloat162float(p[d]) * scale;          // q = q * self.scale (:138)
-    }
+    for (int d = 0; d < kHd; ++d) q[d] = Act<SPLIT>::ld(qkv, s_src[t], 3 * C, head * kHd + d) * scale;   // q = q * self.scale (:138)
     const int ty = t / kWin, tx = t - ty * kWin;
     float sc[kTok];
     float mx = -3.0e38f;
@@ -130,18 +157,16 @@ window_attention_kernel(const __nv_bfloat16 *__restrict__ qkv, int B, int H, int
     const int src = s_src[t];
     const int xo = src % Wp, yo = (src / Wp) % Hp;
     if (yo < H && xo < W) {
-        __nv_bfloat16 *po = out + (((long long)b * H + yo) * W + xo) * C + head * kHd;
+        const long long otok = ((long long)b * H + yo) * W + xo;
 #pragma unroll
-        for (int d = 0; d < kHd; d += 2) {
-            __nv_bfloat162 v2 = __floats2bfloat162_rn(o[d], o[d + 1]);
-            *reinterpret_cast<__nv_bfloat162 *>(po + d) = v2;
-        }
+        for (int d = 0; d < kHd; ++d) Act<SPLIT>::st(out, otok, C, head * kHd + d, o[d]);
     }
 }
 
 // PatchEmbed.proj input rows: NCHW fp32 image -> bf16 [B, ceil(H/4), ceil(W/4), 64], k = c*16 + kh*4 + kw (< 48), zero padded
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
-patch_embed_rows_kernel(const float *__restrict__ img, int B, int H, int W, int Ho, int Wo, __nv_bfloat16 *__restrict__ out)
+patch_embed_rows_kernel(const float *__restrict__ img, int B, int H, int W, int Ho, int Wo, typename Act<SPLIT>::T *__restrict__ out)
 {
     const long long total = (long long)B * Ho * Wo * 64;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -154,32 +179,35 @@ patch_embed_rows_kernel(const float *__restrict__ img, int B, int H, int W, int 
             const int y = oh * 4 + kh, x = ow * 4 + kw;
             if (y < H && x < W) v = img[(((long long)b * 3 + c) * H + y) * W + x];      // F.pad with zeros (:432-436)
         }
-        out[i] = __float2bfloat16_rn(v);
+        Act<SPLIT>::st(out, pix, 64, k, v);
     }
 }
 
 // PatchMerging gather (:288-293): [B,H,W,C] -> [B,ceil(H/2),ceil(W/2),4C] = x(0::2,0::2) | x(1::2,0::2) | x(0::2,1::2) | x(1::2,1::2)
+// (16-bit elements of either format; P = planes per token: 1 bf16, 2 split - the hi and lo planes are gathered alike)
 __global__ void __launch_bounds__(256)
-patch_merge_gather_kernel(const __nv_bfloat16 *__restrict__ x, int B, int H, int W, int C, int Ho, int Wo,
-                          __nv_bfloat16 *__restrict__ y)
+patch_merge_gather_kernel(const uint16_t *__restrict__ x, int B, int H, int W, int C, int P, int Ho, int Wo,
+                          uint16_t *__restrict__ y)
 {
     const int c8 = C / 8;
-    const long long total = (long long)B * Ho * Wo * 4 * c8;
+    const long long total = (long long)B * Ho * Wo * P * 4 * c8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int cc = (int)(i % c8);
         const int part = (int)((i / c8) & 3);
-        const long long pix = i / (4LL * c8);
+        const int pl = (int)((i / (4LL * c8)) % P);
+        const long long pix = i / (4LL * c8 * P);
         const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
         const int yy = oh * 2 + (part & 1), xx = ow * 2 + (part >> 1);
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (yy < H && xx < W) v = *reinterpret_cast<const uint4 *>(x + (((long long)b * H + yy) * W + xx) * C + cc * 8);
-        *reinterpret_cast<uint4 *>(y + pix * (4LL * C) + (long long)part * C + cc * 8) = v;
+        if (yy < H && xx < W) v = *reinterpret_cast<const uint4 *>(x + ((((long long)b * H + yy) * W + xx) * P + pl) * C + cc * 8);
+        *reinterpret_cast<uint4 *>(y + (pix * P + pl) * (4LL * C) + (long long)part * C + cc * 8) = v;
     }
 }
 
 // max_pool2d(kernel_size=1, stride=2) == x[:, ::2, ::2, :]
 __global__ void __launch_bounds__(256)
-subsample2_kernel(const __nv_bfloat16 *__restrict__ x, int B, int H, int W, int C, int Ho, int Wo, __nv_bfloat16 *__restrict__ y)
+subsample2_kernel(const uint16_t *__restrict__ x, int B, int H, int W, int C /* 16-bit elements per token, planes included */, int Ho, int Wo,
+                  uint16_t *__restrict__ y)
 {
     const int c8 = C / 8;
     const long long total = (long long)B * Ho * Wo * c8;
@@ -203,65 +231,114 @@ int grid_for(long long items, int threads)
 
 using namespace orp;
 
-extern "C" int orp_layernorm_bf16(const void *x, int B, int H, int W, int C, const float *gamma, const float *beta, float eps,
-                                  int Hp, int Wp, void *y, void *stream)
+template <bool SPLIT>
+static int layernorm_impl(const void *x, int B, int H, int W, int C, const float *gamma, const float *beta, float eps, int Hp, int Wp,
+                          void *y, void *stream)
 {
-    if (!x || !y || !gamma || !beta || C < 1 || C > 3072 || Hp < H || Wp < W) return fail(ORP_EINVAL, "layernorm_bf16: bad arguments");
+    if (!x || !y || !gamma || !beta || C < 1 || C > 3072 || Hp < H || Wp < W) return fail(ORP_EINVAL, "layernorm: bad arguments");
     int rc = ensure_device();
     if (rc) return rc;
     const long long ntok = (long long)B * H * W;
-    layernorm_bf16_kernel<<<(unsigned)((ntok + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16 *>(x), B, H, W, C, gamma, beta, eps, Hp, Wp, static_cast<__nv_bfloat16 *>(y));
+    typedef typename Act<SPLIT>::T T;
+    layernorm_kernel<SPLIT><<<(unsigned)((ntok + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const T *>(x), B, H, W, C, gamma, beta, eps, Hp, Wp, static_cast<T *>(y));
     ORP_LAUNCHED();
     return ORP_OK;
 }
+extern "C" int orp_layernorm_bf16(const void *x, int B, int H, int W, int C, const float *gamma, const float *beta, float eps,
+                                  int Hp, int Wp, void *y, void *stream)
+{
+    return layernorm_impl<false>(x, B, H, W, C, gamma, beta, eps, Hp, Wp, y, stream);
+}
+extern "C" int orp_layernorm_f16x3(const void *x, int B, int H, int W, int C, const float *gamma, const float *beta, float eps,
+                                   int Hp, int Wp, void *y, void *stream)
+{
+    return layernorm_impl<true>(x, B, H, W, C, gamma, beta, eps, Hp, Wp, y, stream);
+}
 
-extern "C" int orp_window_attention_bf16(const void *qkv, int B, int H, int W, int Hp, int Wp, int C, int heads, int shift,
-                                         const float *bias_table, float scale, void *out, void *stream)
+template <bool SPLIT>
+static int window_attention_impl(const void *qkv, int B, int H, int W, int Hp, int Wp, int C, int heads, int shift,
+                                 const float *bias_table, float scale, void *out, void *stream)
 {
     if (!qkv || !out || !bias_table || heads * kHd != C || Hp % kWin || Wp % kWin || shift < 0 || shift >= kWin)
-        return fail(ORP_EINVAL, "window_attention_bf16: needs 7x7 windows, head_dim 32, padded grid");
+        return fail(ORP_EINVAL, "window_attention: needs 7x7 windows, head_dim 32, padded grid");
     int rc = ensure_device();
     if (rc) return rc;
     dim3 grid(B * (Hp / kWin) * (Wp / kWin), heads);
-    window_attention_kernel<<<grid, 64, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16 *>(qkv), B, H, W, Hp, Wp, C, heads, shift, bias_table, scale, static_cast<__nv_bfloat16 *>(out));
+    typedef typename Act<SPLIT>::T T;
+    window_attention_kernel<SPLIT><<<grid, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const T *>(qkv), B, H, W, Hp, Wp, C, heads, shift, bias_table, scale, static_cast<T *>(out));
     ORP_LAUNCHED();
     return ORP_OK;
 }
-
-extern "C" int orp_patch_embed_rows_bf16(const float *img_nchw, int B, int H, int W, void *out, void *stream)
+extern "C" int orp_window_attention_bf16(const void *qkv, int B, int H, int W, int Hp, int Wp, int C, int heads, int shift,
+                                         const float *bias_table, float scale, void *out, void *stream)
 {
-    if (!img_nchw || !out) return fail(ORP_EINVAL, "patch_embed_rows_bf16: bad arguments");
+    return window_attention_impl<false>(qkv, B, H, W, Hp, Wp, C, heads, shift, bias_table, scale, out, stream);
+}
+extern "C" int orp_window_attention_f16x3(const void *qkv, int B, int H, int W, int Hp, int Wp, int C, int heads, int shift,
+                                          const float *bias_table, float scale, void *out, void *stream)
+{
+    return window_attention_impl<true>(qkv, B, H, W, Hp, Wp, C, heads, shift, bias_table, scale, out, stream);
+}
+
+template <bool SPLIT>
+static int patch_embed_rows_impl(const float *img_nchw, int B, int H, int W, void *out, void *stream)
+{
+    if (!img_nchw || !out) return fail(ORP_EINVAL, "patch_embed_rows: bad arguments");
     int rc = ensure_device();
     if (rc) return rc;
     const int Ho = (H + 3) / 4, Wo = (W + 3) / 4;
-    patch_embed_rows_kernel<<<grid_for((long long)B * Ho * Wo * 64, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        img_nchw, B, H, W, Ho, Wo, static_cast<__nv_bfloat16 *>(out));
+    patch_embed_rows_kernel<SPLIT><<<grid_for((long long)B * Ho * Wo * 64, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        img_nchw, B, H, W, Ho, Wo, static_cast<typename Act<SPLIT>::T *>(out));
     ORP_LAUNCHED();
     return ORP_OK;
 }
-
-extern "C" int orp_patch_merge_gather_bf16(const void *x, int B, int H, int W, int C, void *y, void *stream)
+extern "C" int orp_patch_embed_rows_bf16(const float *img_nchw, int B, int H, int W, void *out, void *stream)
 {
-    if (!x || !y || C % 8) return fail(ORP_EINVAL, "patch_merge_gather_bf16: bad arguments");
+    return patch_embed_rows_impl<false>(img_nchw, B, H, W, out, stream);
+}
+extern "C" int orp_patch_embed_rows_f16x3(const float *img_nchw, int B, int H, int W, void *out, void *stream)
+{
+    return patch_embed_rows_impl<true>(img_nchw, B, H, W, out, stream);
+}
+
+static int patch_merge_gather_impl(const void *x, int B, int H, int W, int C, int P, void *y, void *stream)
+{
+    if (!x || !y || C % 8) return fail(ORP_EINVAL, "patch_merge_gather: bad arguments");
     int rc = ensure_device();
     if (rc) return rc;
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-    patch_merge_gather_kernel<<<grid_for((long long)B * Ho * Wo * 4 * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16 *>(x), B, H, W, C, Ho, Wo, static_cast<__nv_bfloat16 *>(y));
+    patch_merge_gather_kernel<<<grid_for((long long)B * Ho * Wo * P * 4 * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint16_t *>(x), B, H, W, C, P, Ho, Wo, static_cast<uint16_t *>(y));
     ORP_LAUNCHED();
     return ORP_OK;
 }
-
-extern "C" int orp_subsample2_bf16(const void *x, int B, int H, int W, int C, void *y, void *stream)
+extern "C" int orp_patch_merge_gather_bf16(const void *x, int B, int H, int W, int C, void *y, void *stream)
 {
-    if (!x || !y || C % 8) return fail(ORP_EINVAL, "subsample2_bf16: bad arguments");
+    return patch_merge_gather_impl(x, B, H, W, C, 1, y, stream);
+}
+extern "C" int orp_patch_merge_gather_f16x3(const void *x, int B, int H, int W, int C, void *y, void *stream)
+{
+    return patch_merge_gather_impl(x, B, H, W, C, 2, y, stream);
+}
+
+static int subsample2_impl(const void *x, int B, int H, int W, int Cel, void *y, void *stream)
+{
+    if (!x || !y || Cel % 8) return fail(ORP_EINVAL, "subsample2: bad arguments");
     int rc = ensure_device();
     if (rc) return rc;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-    subsample2_kernel<<<grid_for((long long)B * Ho * Wo * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16 *>(x), B, H, W, C, Ho, Wo, static_cast<__nv_bfloat16 *>(y));
+    subsample2_kernel<<<grid_for((long long)B * Ho * Wo * (Cel / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint16_t *>(x), B, H, W, Cel, Ho, Wo, static_cast<uint16_t *>(y));
     ORP_LAUNCHED();
     return ORP_OK;
+}
+extern "C" int orp_subsample2_bf16(const void *x, int B, int H, int W, int C, void *y, void *stream)
+{
+    return subsample2_impl(x, B, H, W, C, y, stream);
+}
+extern "C" int orp_subsample2_f16x3(const void *x, int B, int H, int W, int C, void *y, void *stream)
+{
+    return subsample2_impl(x, B, H, W, 2 * C, y, stream);       // a split token is 2 C contiguous 16-bit elements
 }

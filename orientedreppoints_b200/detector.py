@@ -194,8 +194,8 @@ class OrientedRepPointsDetector:
         """Swin-T + FPN(in [192,384,768], start_level 0, no extra convs: P6/P7 = stride-2 subsampling, fpn.py:163-165)"""
         from .swin import SwinTiny
         d = self.device
-        if self.eng.name != "bf16":
-            raise ValueError("the Swin-T backbone runs on the bf16 tensor-core engine")
+        if self.eng.name not in ("bf16", "f16x3"):
+            raise ValueError("the Swin-T backbone runs on the tensor-core engines ('f16x3' or 'bf16')")
         self.swin = SwinTiny(sd, d, self.eng)
         self.lat = [(ConvLayer(sd["neck.lateral_convs.%d.conv.weight" % i].float(), None, 1, 0, d),
                      Norm(sd, "neck.lateral_convs.%d.gn" % i, d)) for i in range(3)]

@@ -238,6 +238,17 @@ class EngineTC:
     def from_float(self, x):
         return x.to(self.device, torch.bfloat16).contiguous()
 
+    suffix = "bf16"                                      # C-ABI entry points of this engine's activation format
+
+    def alloc(self, b, h, w, c, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return f((b, h, w, c), dtype=torch.bfloat16, device=self.device)
+
+    @staticmethod
+    def dims(x):
+        """(B, H, W, C) of an activation tensor of this engine"""
+        return tuple(x.shape)
+
 
 class EngineTCSplit(EngineTC):
     """f16x3 arithmetic on the same tcgen05 kernels - the PARITY mode (include/orp_b200.h, "split" section): every fp32
@@ -267,7 +278,8 @@ class EngineTCSplit(EngineTC):
         if getattr(L, "tc3", None) is None:
             w = L.w_raw                                              # [Cout, KH, KW, Cin] fp32 (unpadded Cin)
             cout, kh, kw, cin = w.shape
-            cout_p = ((cout + 31) // 32) * 32
+            # weight rows: a multiple of 64 (TMA-store epilogue tiles; Swin's 96 / 288 channels), 32 for the small fp32 heads
+            cout_p = ((cout + 31) // 32) * 32 if cout <= 32 else ((cout + 63) // 64) * 64
             cin_p = ((cin + 63) // 64) * 64
             wp4 = torch.zeros((cout_p, kh * kw, cin_p), dtype=torch.float32)
             wp4[:cout, :, :cin] = w.reshape(cout, kh * kw, cin)
@@ -309,6 +321,17 @@ class EngineTCSplit(EngineTC):
         y = torch.empty((n, h, w, 2, c), dtype=torch.float16, device=self.device)
         _lib.check(self.lib.orp_split_from_f32(_lib.ptr(x), n * h * w, c, _lib.ptr(y), _lib.current_stream_ptr()), "orp_split_from_f32")
         return y
+
+    suffix = "f16x3"
+
+    def alloc(self, b, h, w, c, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return f((b, h, w, 2, c), dtype=torch.float16, device=self.device)
+
+    @staticmethod
+    def dims(x):
+        b, h, w, _, c = x.shape
+        return b, h, w, c
 
     def overflow_count(self, reset=True):
         c = ctypes.c_uint(0)

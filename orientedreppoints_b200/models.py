@@ -233,8 +233,7 @@ class OrientedRepPointsDetector(nn.Module):
             if dev.type != 'cuda':
                 raise NotImplementedError("OrientedRepPointsDetector inference needs a CUDA (sm_100a) device: there is no CPU path")
             depth = self.backbone.depth if isinstance(self.backbone, ResNet) else "swin_tiny"
-            prec = self.precision if depth != "swin_tiny" else "bf16"
-            self._engine = Engine({k: v.detach() for k, v in self.state_dict().items()}, depth, dev, prec,
+            self._engine = Engine({k: v.detach() for k, v in self.state_dict().items()}, depth, dev, self.precision,
                                   test_cfg=dict(self.test_cfg) if self.test_cfg else None)
         return self._engine
 

@@ -102,28 +102,29 @@ class SwinTiny:
         self.out_norms = {i: _LN(sd, "backbone.norm%d" % i, device) for i in (1, 2, 3)}
 
     # ------------------------------------------------------------------ primitive launches
+    # (the engine decides the activation format: bf16 [B,H,W,C] or split fp16 [B,H,W,2,C]; `e.suffix` picks the entry points)
+    def _fn(self, name):
+        return getattr(self.lib, "orp_%s_%s" % (name, self.e.suffix))
+
     def _ln(self, x, norm, hp=None, wp=None):
-        b, h, w, c = x.shape
+        b, h, w, c = self.e.dims(x)
         hp, wp = hp or h, wp or w
-        if (hp, wp) != (h, w):
-            y = torch.zeros((b, hp, wp, c), dtype=torch.bfloat16, device=self.dev)        # F.pad zeros after norm1
-        else:
-            y = torch.empty((b, h, w, c), dtype=torch.bfloat16, device=self.dev)
-        _lib.check(self.lib.orp_layernorm_bf16(_lib.ptr(x), b, h, w, c, _lib.ptr(norm.gamma), _lib.ptr(norm.beta), 1e-5, hp, wp,
-                                               _lib.ptr(y), _lib.current_stream_ptr()), "orp_layernorm_bf16")
+        y = self.e.alloc(b, hp, wp, c, zero=(hp, wp) != (h, w))                            # F.pad zeros after norm1
+        _lib.check(self._fn("layernorm")(_lib.ptr(x), b, h, w, c, _lib.ptr(norm.gamma), _lib.ptr(norm.beta), 1e-5, hp, wp,
+                                         _lib.ptr(y), _lib.current_stream_ptr()), "orp_layernorm")
         return y
 
     def _attention(self, qkv, b, h, w, c, heads, shift, table):
-        hp, wp = qkv.shape[1], qkv.shape[2]
-        out = torch.empty((b, h, w, c), dtype=torch.bfloat16, device=self.dev)
-        _lib.check(self.lib.orp_window_attention_bf16(_lib.ptr(qkv), b, h, w, hp, wp, c, heads, shift, _lib.ptr(table),
-                                                      float((c // heads) ** -0.5), _lib.ptr(out), _lib.current_stream_ptr()),
-                   "orp_window_attention_bf16")
+        _, hp, wp, _ = self.e.dims(qkv)
+        out = self.e.alloc(b, h, w, c)
+        _lib.check(self._fn("window_attention")(_lib.ptr(qkv), b, h, w, hp, wp, c, heads, shift, _lib.ptr(table),
+                                                float((c // heads) ** -0.5), _lib.ptr(out), _lib.current_stream_ptr()),
+                   "orp_window_attention")
         return out
 
     def block(self, x, blk):
         e = self.e
-        b, h, w, c = x.shape
+        b, h, w, c = e.dims(x)
         hp = (h + WINDOW - 1) // WINDOW * WINDOW
         wp = (w + WINDOW - 1) // WINDOW * WINDOW
         t = self._ln(x, blk["norm1"], hp, wp)
@@ -135,20 +136,20 @@ class SwinTiny:
         return e.conv(hmid, blk["fc2"], residual=x)                                       # x = x + mlp(norm2(x))
 
     def merge(self, x, m):
-        b, h, w, c = x.shape
+        b, h, w, c = self.e.dims(x)
         ho, wo = (h + 1) // 2, (w + 1) // 2
-        g = torch.empty((b, ho, wo, 4 * c), dtype=torch.bfloat16, device=self.dev)
-        _lib.check(self.lib.orp_patch_merge_gather_bf16(_lib.ptr(x), b, h, w, c, _lib.ptr(g), _lib.current_stream_ptr()),
-                   "orp_patch_merge_gather_bf16")
+        g = self.e.alloc(b, ho, wo, 4 * c)
+        _lib.check(self._fn("patch_merge_gather")(_lib.ptr(x), b, h, w, c, _lib.ptr(g), _lib.current_stream_ptr()),
+                   "orp_patch_merge_gather")
         return self.e.conv(self._ln(g, m["norm"]), m["red"])
 
     def forward(self, img):
         img = img.to(self.dev, torch.float32).contiguous()
         b, _, h, w = img.shape
         ho, wo = (h + 3) // 4, (w + 3) // 4
-        rows = torch.empty((b, ho, wo, 64), dtype=torch.bfloat16, device=self.dev)
-        _lib.check(self.lib.orp_patch_embed_rows_bf16(_lib.ptr(img), b, h, w, _lib.ptr(rows), _lib.current_stream_ptr()),
-                   "orp_patch_embed_rows_bf16")
+        rows = self.e.alloc(b, ho, wo, 64)
+        _lib.check(self._fn("patch_embed_rows")(_lib.ptr(img), b, h, w, _lib.ptr(rows), _lib.current_stream_ptr()),
+                   "orp_patch_embed_rows")
         x = self._ln(self.e.conv(rows, self.embed), self.embed_norm)
         outs = []
         for i, stage in enumerate(self.blocks):
@@ -161,7 +162,7 @@ class SwinTiny:
         return outs
 
     def subsample2(self, x):
-        b, h, w, c = x.shape
-        y = torch.empty((b, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=torch.bfloat16, device=self.dev)
-        _lib.check(self.lib.orp_subsample2_bf16(_lib.ptr(x), b, h, w, c, _lib.ptr(y), _lib.current_stream_ptr()), "orp_subsample2_bf16")
+        b, h, w, c = self.e.dims(x)
+        y = self.e.alloc(b, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c)
+        _lib.check(self._fn("subsample2")(_lib.ptr(x), b, h, w, c, _lib.ptr(y), _lib.current_stream_ptr()), "orp_subsample2")
         return y

@@ -25,6 +25,27 @@ template <> struct Act<false> {
     static __device__ __forceinline__ float ld(const T *b, long long tok, int C, int c) { return __bfloat162float(b[tok * C + c]); }
     static __device__ __forceinline__ void st(T *b, long long tok, int C, int c, float v) { b[tok * C + c] = __float2bfloat16_rn(v); }
     static constexpr int planes = 1;
+    // 8 consecutive channels (c % 8 == 0) of one token
+    static __device__ __forceinline__ void ld8(const T *b, long long tok, int C, int c, float (&o)[8])
+    {
+        const uint4 u = *reinterpret_cast<const uint4 *>(b + tok * C + c);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&w[k]));
+            o[2 * k] = f.x; o[2 * k + 1] = f.y;
+        }
+    }
+    static __device__ __forceinline__ void st8(T *b, long long tok, int C, int c, const float (&v)[8])
+    {
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat162 p = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+            w[k] = *reinterpret_cast<uint32_t *>(&p);
+        }
+        *reinterpret_cast<uint4 *>(b + tok * C + c) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
 };
 template <> struct Act<true> {
     typedef __half T;
@@ -42,6 +63,34 @@ template <> struct Act<true> {
         p[C] = __float2half_rn(a - __half2float(h));
     }
     static constexpr int planes = 2;
+    static __device__ __forceinline__ void ld8(const T *b, long long tok, int C, int c, float (&o)[8])
+    {
+        const T *p = b + tok * 2 * C + c;
+        const uint4 uh = *reinterpret_cast<const uint4 *>(p), ul = *reinterpret_cast<const uint4 *>(p + C);
+        const uint32_t wh[4] = {uh.x, uh.y, uh.z, uh.w}, wl[4] = {ul.x, ul.y, ul.z, ul.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 fh = __half22float2(*reinterpret_cast<const __half2 *>(&wh[k]));
+            const float2 fl = __half22float2(*reinterpret_cast<const __half2 *>(&wl[k]));
+            o[2 * k] = fh.x + fl.x; o[2 * k + 1] = fh.y + fl.y;
+        }
+    }
+    static __device__ __forceinline__ void st8(T *b, long long tok, int C, int c, const float (&v)[8])
+    {
+        uint32_t wh[4], wl[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a = fminf(fmaxf(v[2 * k], -65504.f), 65504.f), d = fminf(fmaxf(v[2 * k + 1], -65504.f), 65504.f);
+            const __half2 h2 = __floats2half2_rn(a, d);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(a - hf.x, d - hf.y);
+            wh[k] = *reinterpret_cast<const uint32_t *>(&h2);
+            wl[k] = *reinterpret_cast<const uint32_t *>(&l2);
+        }
+        T *p = b + tok * 2 * C + c;
+        *reinterpret_cast<uint4 *>(p) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+        *reinterpret_cast<uint4 *>(p + C) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+    }
 };
 
 // one warp per token; out may be a padded grid [B,Hp,Wp,C] (rows beyond H,W pre-zeroed by the caller)
@@ -50,28 +99,33 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const typename Act<SPLIT>::T *__restrict__ x, int B, int H, int W, int C, const float *__restrict__ gamma,
                  const float *__restrict__ beta, float eps, int Hp, int Wp, typename Act<SPLIT>::T *__restrict__ y)
 {
+    // one warp per token; a lane owns 16-byte chunks (8 channels) lane, lane + 32, ...: vector loads and stores (C % 8 == 0)
     const int lane = threadIdx.x & 31;
     const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long ntok = (long long)B * H * W;
     if (tok >= ntok) return;
-    float v[96];                                   // C <= 3072
-    const int per = (C + 31) / 32;
+    float v[12][8];                                // C <= 3072: at most 12 chunks per lane
+    const int chunks = C >> 3;
     float s = 0.f;
-#pragma unroll 4
-    for (int i = 0; i < per; ++i) {
-        const int c = lane + i * 32;
-        v[i] = c < C ? Act<SPLIT>::ld(x, tok, C, c) : 0.f;
-        s += v[i];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const int ch = lane + i * 32;
+        if (ch < chunks) {
+            Act<SPLIT>::ld8(x, tok, C, ch * 8, v[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[i][j];
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s / (float)C;
     float q = 0.f;
-#pragma unroll 4
-    for (int i = 0; i < per; ++i) {
-        const int c = lane + i * 32;
-        const float d = c < C ? v[i] - mean : 0.f;
-        q += d * d;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        if (lane + i * 32 < chunks) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
@@ -79,10 +133,18 @@ layernorm_kernel(const typename Act<SPLIT>::T *__restrict__ x, int B, int H, int
     const int b = (int)(tok / ((long long)H * W)), hw = (int)(tok - (long long)b * H * W);
     const int h = hw / W, w = hw - h * W;
     const long long otok = ((long long)b * Hp + h) * Wp + w;
-#pragma unroll 4
-    for (int i = 0; i < per; ++i) {
-        const int c = lane + i * 32;
-        if (c < C) Act<SPLIT>::st(y, otok, C, c, (v[i] - mean) * rstd * gamma[c] + beta[c]);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const int ch = lane + i * 32;
+        if (ch < chunks) {
+            const float4 g0 = *reinterpret_cast<const float4 *>(gamma + ch * 8), g1 = *reinterpret_cast<const float4 *>(gamma + ch * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4 *>(beta + ch * 8), b1 = *reinterpret_cast<const float4 *>(beta + ch * 8 + 4);
+            const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float o8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o8[j] = (v[i][j] - mean) * rstd * ga[j] + be[j];
+            Act<SPLIT>::st8(y, otok, C, ch * 8, o8);
+        }
     }
 }
 
@@ -96,8 +158,11 @@ window_attention_kernel(const typename Act<SPLIT>::T *__restrict__ qkv, int B, i
                         int shift, const float *__restrict__ bias_table /* [169, heads] */, float scale,
                         typename Act<SPLIT>::T *__restrict__ out)
 {
-    __shared__ float sk[kTok][kHd + 1], sv[kTok][kHd + 1];
+    // K and V of the window's 49 tokens in shared memory as float4 rows: every thread reads the same key at the same time
+    // (a broadcast, conflict free), 8 LDS.128 per 32 multiply-adds
+    __shared__ __align__(16) float sk[kTok][kHd], sv[kTok][kHd];
     __shared__ int s_src[kTok], s_reg[kTok];
+    __shared__ float s_bias[169];
     const int nww = Wp / kWin, nwh = Hp / kWin;
     const int head = blockIdx.y;
     const int wid = blockIdx.x % (nwh * nww), b = blockIdx.x / (nwh * nww);
@@ -115,43 +180,61 @@ window_attention_kernel(const typename Act<SPLIT>::T *__restrict__ qkv, int B, i
         const int wr = xs < Wp - kWin ? 0 : (xs < Wp - shift ? 1 : 2);
         s_reg[t] = shift > 0 ? hr * 3 + wr : 0;
     }
+    for (int i = t; i < 169; i += 64) s_bias[i] = bias_table[i * heads + head];
     __syncthreads();
-    for (int e = t; e < kTok * kHd; e += 64) {
-        const int j = e / kHd, d = e - j * kHd;
-        sk[j][d] = Act<SPLIT>::ld(qkv, s_src[j], 3 * C, C + head * kHd + d);
-        sv[j][d] = Act<SPLIT>::ld(qkv, s_src[j], 3 * C, 2 * C + head * kHd + d);
+    for (int e = t; e < kTok * 4; e += 64) {                               // (token, 8-channel chunk)
+        const int j = e >> 2, d8 = (e & 3) * 8;
+        float kk[8], vv[8];
+        Act<SPLIT>::ld8(qkv, s_src[j], 3 * C, C + head * kHd + d8, kk);
+        Act<SPLIT>::ld8(qkv, s_src[j], 3 * C, 2 * C + head * kHd + d8, vv);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) { sk[j][d8 + d] = kk[d]; sv[j][d8 + d] = vv[d]; }
     }
     __syncthreads();
     if (t >= kTok) return;
     float q[kHd];
 #pragma unroll
-    for (int d = 0; d < kHd; ++d) q[d] = Act<SPLIT>::ld(qkv, s_src[t], 3 * C, head * kHd + d) * scale;   // q = q * self.scale (:138)
+    for (int d8 = 0; d8 < kHd; d8 += 8) {
+        float qq[8];
+        Act<SPLIT>::ld8(qkv, s_src[t], 3 * C, head * kHd + d8, qq);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) q[d8 + d] = qq[d] * scale;               // q = q * self.scale (:138)
+    }
     const int ty = t / kWin, tx = t - ty * kWin;
     float sc[kTok];
     float mx = -3.0e38f;
-#pragma unroll 7
+#pragma unroll
     for (int j = 0; j < kTok; ++j) {
         float a = 0.f;
+        const float4 *kr = reinterpret_cast<const float4 *>(sk[j]);
 #pragma unroll
-        for (int d = 0; d < kHd; ++d) a = fmaf(q[d], sk[j][d], a);
+        for (int d4 = 0; d4 < kHd / 4; ++d4) {
+            const float4 k4 = kr[d4];
+            a = fmaf(q[4 * d4], k4.x, a); a = fmaf(q[4 * d4 + 1], k4.y, a); a = fmaf(q[4 * d4 + 2], k4.z, a); a = fmaf(q[4 * d4 + 3], k4.w, a);
+        }
         const int jy = j / kWin, jx = j - jy * kWin;
-        a += bias_table[((ty - jy + kWin - 1) * (2 * kWin - 1) + (tx - jx + kWin - 1)) * heads + head];   // :107-118, :141-144
+        a += s_bias[(ty - jy + kWin - 1) * (2 * kWin - 1) + (tx - jx + kWin - 1)];                       // :107-118, :141-144
         if (s_reg[t] != s_reg[j]) a += -100.0f;                                                            // :388-389
         sc[j] = a;
         mx = fmaxf(mx, a);
     }
     float den = 0.f;
-#pragma unroll 7
+#pragma unroll
     for (int j = 0; j < kTok; ++j) { sc[j] = expf(sc[j] - mx); den += sc[j]; }
     const float inv = 1.0f / den;
     float o[kHd];
 #pragma unroll
     for (int d = 0; d < kHd; ++d) o[d] = 0.f;
-#pragma unroll 7
+#pragma unroll
     for (int j = 0; j < kTok; ++j) {
         const float pj = sc[j] * inv;
+        const float4 *vr = reinterpret_cast<const float4 *>(sv[j]);
 #pragma unroll
-        for (int d = 0; d < kHd; ++d) o[d] = fmaf(pj, sv[j][d], o[d]);
+        for (int d4 = 0; d4 < kHd / 4; ++d4) {
+            const float4 v4 = vr[d4];
+            o[4 * d4] = fmaf(pj, v4.x, o[4 * d4]); o[4 * d4 + 1] = fmaf(pj, v4.y, o[4 * d4 + 1]);
+            o[4 * d4 + 2] = fmaf(pj, v4.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(pj, v4.w, o[4 * d4 + 3]);
+        }
     }
     // window_reverse + roll(+shift) + crop: the token returns to its original position if that is inside H x W
     const int src = s_src[t];
@@ -159,7 +242,10 @@ window_attention_kernel(const typename Act<SPLIT>::T *__restrict__ qkv, int B, i
     if (yo < H && xo < W) {
         const long long otok = ((long long)b * H + yo) * W + xo;
 #pragma unroll
-        for (int d = 0; d < kHd; ++d) Act<SPLIT>::st(out, otok, C, head * kHd + d, o[d]);
+        for (int d8 = 0; d8 < kHd; d8 += 8) {
+            const float o8[8] = {o[d8], o[d8 + 1], o[d8 + 2], o[d8 + 3], o[d8 + 4], o[d8 + 5], o[d8 + 6], o[d8 + 7]};
+            Act<SPLIT>::st8(out, otok, C, head * kHd + d8, o8);
+        }
     }
 }
 
@@ -235,7 +321,7 @@ template <bool SPLIT>
 static int layernorm_impl(const void *x, int B, int H, int W, int C, const float *gamma, const float *beta, float eps, int Hp, int Wp,
                           void *y, void *stream)
 {
-    if (!x || !y || !gamma || !beta || C < 1 || C > 3072 || Hp < H || Wp < W) return fail(ORP_EINVAL, "layernorm: bad arguments");
+    if (!x || !y || !gamma || !beta || C < 8 || C > 3072 || (C & 7) || Hp < H || Wp < W) return fail(ORP_EINVAL, "layernorm: C must be a multiple of 8, <= 3072");
     int rc = ensure_device();
     if (rc) return rc;
     const long long ntok = (long long)B * H * W;

@@ -630,6 +630,15 @@ nms_resolve_lazy_kernel(LazyParams P)
         for (unsigned int w = gwarp; w < nsrc; w += nwarps) {
             const int r = round == 0 ? (int)w : src[w];
             if (P.status[r] != 0) continue;
+            if (round == 0) {
+                // nothing is kept yet: a box without candidates is kept, every other box waits - no need to walk its list
+                if (lane == 0) {
+                    if (P.len[r] == 0) P.status[r] = 1;
+                    else dst[atomicAdd(&P.wcount[0], 1u)] = r;
+                }
+                local = 1;
+                continue;
+            }
             const int b = P.offs[r], e = b + P.len[r];
             bool pend = false, undec = false;
             int outpos = b;                                  // in-place compaction: writes never pass the chunk being read

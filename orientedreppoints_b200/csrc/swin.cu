@@ -97,45 +97,46 @@ template <> struct Act<true> {
 template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const typename Act<SPLIT>::T *__restrict__ x, int B, int H, int W, int C, const float *__restrict__ gamma,
-                 const float *__restrict__ beta, float eps, int Hp, int Wp, typename Act<SPLIT>::T *__restrict__ y)
+                 const float *__restrict__ beta, float eps, int Hp, int Wp, int G, typename Act<SPLIT>::T *__restrict__ y)
 {
-    // one warp per token; a lane owns 16-byte chunks (8 channels) lane, lane + 32, ...: vector loads and stores (C % 8 == 0)
-    const int lane = threadIdx.x & 31;
-    const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // a group of G lanes (G = power of two >= C / 8, at most 32) per token, 32 / G tokens per warp; a lane owns the 16-byte chunks
+    // (8 channels) g, g + G, ... of its token: vector loads and stores, all lanes busy for the narrow stages (C = 96: G = 16)
+    const int lane = threadIdx.x & 31, g = lane & (G - 1);
+    const int tpw = 32 / G;                                                    // tokens per warp
+    const long long tok = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * tpw + lane / G;
     const long long ntok = (long long)B * H * W;
-    if (tok >= ntok) return;
+    const bool live = tok < ntok;
     float v[12][8];                                // C <= 3072: at most 12 chunks per lane
     const int chunks = C >> 3;
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
-        const int ch = lane + i * 32;
-        if (ch < chunks) {
+        const int ch = g + i * G;
+        if (live && ch < chunks) {
             Act<SPLIT>::ld8(x, tok, C, ch * 8, v[i]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) s += v[i][j];
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s / (float)C;
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
-        if (lane + i * 32 < chunks) {
+        if (live && g + i * G < chunks) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    for (int o = G >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (!live) return;
     const float rstd = rsqrtf(q / (float)C + eps);
     const int b = (int)(tok / ((long long)H * W)), hw = (int)(tok - (long long)b * H * W);
     const int h = hw / W, w = hw - h * W;
     const long long otok = ((long long)b * Hp + h) * Wp + w;
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
-        const int ch = lane + i * 32;
+        const int ch = g + i * G;
         if (ch < chunks) {
             const float4 g0 = *reinterpret_cast<const float4 *>(gamma + ch * 8), g1 = *reinterpret_cast<const float4 *>(gamma + ch * 8 + 4);
             const float4 b0 = *reinterpret_cast<const float4 *>(beta + ch * 8), b1 = *reinterpret_cast<const float4 *>(beta + ch * 8 + 4);
@@ -326,8 +327,11 @@ static int layernorm_impl(const void *x, int B, int H, int W, int C, const float
     if (rc) return rc;
     const long long ntok = (long long)B * H * W;
     typedef typename Act<SPLIT>::T T;
-    layernorm_kernel<SPLIT><<<(unsigned)((ntok + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const T *>(x), B, H, W, C, gamma, beta, eps, Hp, Wp, static_cast<T *>(y));
+    int G = 1;
+    while (G < 32 && G < (C >> 3)) G <<= 1;
+    const long long tok_per_block = 8LL * (32 / G);
+    layernorm_kernel<SPLIT><<<(unsigned)((ntok + tok_per_block - 1) / tok_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const T *>(x), B, H, W, C, gamma, beta, eps, Hp, Wp, G, static_cast<T *>(y));
     ORP_LAUNCHED();
     return ORP_OK;
 }

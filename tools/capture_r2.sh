@@ -25,3 +25,6 @@ ncu --set full --clock-control none --import-source on -k regex:nms_resolve_lazy
 python tools/trace_tc.py 1 f16x3 > $O/trace_f16x3_b1.log 2>&1
 ORP_TC_TRACE=1 python tools/trace_tc.py 1 f16x3 2>&1 | grep "^tc\[" > $O/trace_f16x3_b1_launches.log
 tail -n 3 $O/trace_f16x3_b1.log
+# 5. Swin-T (f16x3, 8 tiles): every launch of one dense step
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/r2_launches_swin_f16x3_b8.csv python tools/trace_tc.py 8 f16x3 swin_tiny > $O/cap9.log 2>&1
+ORP_TC_TRACE=1 python tools/trace_tc.py 16 f16x3 2>&1 | grep "^tc\[" > $O/trace_f16x3_b16_launches.log

@@ -250,26 +250,40 @@ nms_gather_kernel(const float *__restrict__ dets, const int32_t *__restrict__ se
 // ---------------------------------------------------------------------------------------------
 struct Quad { float c[8]; };
 
-__device__ __noinline__ bool decide_fp64(const Quad &A, const Quad &B, double thr, int union_mode)
+// The reference's fp64 arithmetic for one pair, evaluated by a whole warp: its 16 (edge of A, edge of B) fan terms are
+// independent, so lane l < 16 computes term (l / 4, l % 4) and the terms are then added in the reference's order
+// (polyiou.cpp:122-131: i outer, j inner) - same bits as the serial loop at 1/16 of its latency.  Every lane of the
+// warp must call it with the same quads.
+__device__ __noinline__ bool decide_fp64_warp(const Quad &A, const Quad &B, double thr, int union_mode, int lane)
 {
-    double p[8], q[8];
+    using R = Rn<double>;
+    Pt<double> P[6], Q[6];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { p[k] = (double)A.c[k]; q[k] = (double)B.c[k]; }
-    PairRes<double> r = ref_quad_pair<double>(p, q);
-    double iou = iou_from<double>(r, union_mode);
+    for (int i = 0; i < 4; ++i) {
+        P[i].x = (double)A.c[2 * i]; P[i].y = (double)A.c[2 * i + 1];
+        Q[i].x = (double)B.c[2 * i]; Q[i].y = (double)B.c[2 * i + 1];
+    }
+    if (ring_area(P, 4) < 0) { Pt<double> t = P[0]; P[0] = P[3]; P[3] = t; t = P[1]; P[1] = P[2]; P[2] = t; }
+    if (ring_area(Q, 4) < 0) { Pt<double> t = Q[0]; Q[0] = Q[3]; Q[3] = t; t = Q[1]; Q[1] = Q[2]; Q[2] = t; }
+    P[4] = P[0]; Q[4] = Q[0];
+    const int i = (lane >> 2) & 3, j = lane & 3;
+    const double v = fan_pair(P[i], P[i + 1], Q[j], Q[j + 1]);
+    PairRes<double> r;
+    r.inter = 0;
+    for (int k = 0; k < 16; ++k) r.inter = R::add(r.inter, __shfl_sync(0xffffffffu, v, k));
+    const double ap = ring_area(P, 4), aq = ring_area(Q, 4);
+    r.area_p = ap < 0 ? -ap : ap;
+    r.area_q = aq < 0 ? -aq : aq;
+    const double iou = iou_from<double>(r, union_mode);
     return suppresses<double>(iou, thr, union_mode);
 }
 
-// returns true iff the reference's fp64 IoU of (A,B) suppresses at thr
-template <int S>
-__device__ __forceinline__ bool decide_exact(const Quad &A, const Quad &B, const float4 &ba,
-                                             const float4 &bb, bool both_convex, double thr,
-                                             int union_mode, bool &used64, float *scratch)
+// 1 / 0: the reference's fp64 IoU of (A, B) certainly suppresses / does not suppress at thr (fp32 clip with an error band);
+// -1: inside the band, or not a pair of convex quadrilaterals -> decide_fp64_warp
+__device__ __forceinline__ int decide_fast(const Quad &A, const Quad &B, const float4 &ba, const float4 &bb, bool both_convex,
+                                           double thr, float *scratch)
 {
-    if (!both_convex) {
-        used64 = true;
-        return decide_fp64(A, B, thr, union_mode);
-    }
+    if (!both_convex) return -1;
     const float ox = 0.5f * (fmaxf(ba.x, bb.x) + fminf(ba.z, bb.z));
     const float oy = 0.5f * (fmaxf(ba.y, bb.y) + fminf(ba.w, bb.w));
     float a[8], b[8];
@@ -278,14 +292,12 @@ __device__ __forceinline__ bool decide_exact(const Quad &A, const Quad &B, const
         a[2 * k] = A.c[2 * k] - ox; a[2 * k + 1] = A.c[2 * k + 1] - oy;
         b[2 * k] = B.c[2 * k] - ox; b[2 * k + 1] = B.c[2 * k + 1] - oy;
     }
-    FastRes r = fast_quad_pair_s<S>(a, b, scratch);
+    FastRes r = fast_quad_pair_s<1>(a, b, scratch);
     const float t = (float)thr;
     const float margin = r.inter * (1.f + t) - t * (r.area_a + r.area_b);
     const float band = 4.f * r.err + 1e-6f * (r.area_a + r.area_b);
-    used64 = false;
-    if (fabsf(margin) > band) return margin > 0.f;
-    used64 = true;
-    return decide_fp64(A, B, thr, union_mode);
+    if (fabsf(margin) > band) return margin > 0.f ? 1 : 0;
+    return -1;
 }
 
 struct SweepParams {
@@ -297,8 +309,9 @@ struct SweepParams {
     const int32_t *nvalid;
     const NmsGlobal *G;
     int R;
-    int2 *edges;
-    int32_t *indeg;
+    int2 *edges;                               // (better-ranked box, worse-ranked box)
+    int32_t *outdeg;                           // per better box: how many worse boxes list it as a candidate
+    int32_t *pending;                          // per worse box: candidates not resolved yet
     unsigned long long edge_cap;
     NmsCounters *ctr;
     double thr;
@@ -338,7 +351,7 @@ __device__ __forceinline__ bool frame_prune(const float *p, const float *q, floa
 // One warp per registration slot i: walk the slots after it while they stay in the same (segment, strip) group and
 // start left of i's right edge; lanes test AABBs (coalesced float4 reads of the sorted array), survivors of the area bound
 // are compacted into a per-warp shared-memory queue, filtered by the projection bounds in both boxes' frames, and emitted
-// as candidate pairs (worse-ranked box, better-ranked box) by ORIGINAL index.
+// as candidate pairs (better-ranked box, worse-ranked box) by ORIGINAL index.
 __global__ void __launch_bounds__(kSweepWarps * 32, 6)
 nms_sweep_kernel(SweepParams P)
 {
@@ -425,8 +438,9 @@ nms_sweep_kernel(SweepParams P)
                         const bool i_worse = rk_i > P.rank[bj];
                         const int lo = i_worse ? bi : bj, hi = i_worse ? bj : bi;
                         if (pos < P.edge_cap) {
-                            P.edges[pos] = make_int2(lo, hi);
-                            atomicAdd(&P.indeg[lo], 1);
+                            P.edges[pos] = make_int2(hi, lo);
+                            atomicAdd(&P.outdeg[hi], 1);
+                            atomicAdd(&P.pending[lo], 1);
                         } else {
                             P.ctr->overflow = 1;
                         }
@@ -581,34 +595,44 @@ nms_resolve_kernel(const int32_t *__restrict__ offs, const int32_t *__restrict__
     if (tid == 0) ctr->rounds = round;
 }
 
-// Lazy variant (EXACT64 mode): adj holds CANDIDATE pairs by sweep slot; a candidate is clipped only when its better-ranked
-// box is known to be kept and the worse one is still undecided.  Per round:
-//   phase A (warp per undecided box): scan the candidate list, dropping entries that can no longer matter (suppressed
-//            candidates, pairs already proven harmless) so that later rounds only touch live entries; kept candidates not
-//            evaluated yet go to a global work queue; a box with nothing queued and no undecided candidate left is kept.
-//   phase B (thread per queue entry): decide the pair exactly; "suppresses" -> the box is suppressed, otherwise the
-//            candidate is struck from the list (adj = -1).
-// Statuses only move undecided -> final and a box is decided from final statuses only, so the fixed point is the greedy
-// result whatever the evaluation order.
+// Lazy variant (EXACT64 mode).  The sweep leaves CANDIDATE pairs; a candidate is clipped only when its better-ranked box is
+// known to be kept and the worse one is still undecided, and nothing is ever scanned twice: the graph is stored by the
+// BETTER box (out lists of worse boxes) and every box carries `pending` = candidates not resolved yet.  Decisions travel
+// along the out lists of the boxes decided in the previous round (two frontiers):
+//   phase 1 (warp per frontier box): a newly KEPT box queues (worse box, itself) for clipping, for every undecided worse box;
+//            a newly SUPPRESSED box resolves itself in its worse boxes (pending -= 1);
+//   phase 2 (thread per queued pair): decide the pair exactly; "suppresses" -> the worse box is suppressed (first writer joins
+//            the suppressed frontier), otherwise the pair is resolved (pending -= 1).
+// pending reaching 0 means every better candidate is suppressed or proven harmless: the box is kept (exactly one decrement
+// sees 1 -> 0, and a box with a suppressing pair never gets there because that pair is never resolved).  Statuses only move
+// undecided -> final and each decision uses final statuses only, so the fixed point is the greedy result whatever the order.
+// Total work is O(candidates) + the clips, instead of a rescan of every live list per round.
 struct LazyParams {
-    const int32_t *offs;
-    int32_t *adj;
+    const int32_t *offs;                       // out lists: offs[j] .. offs[j] + deg[j]
+    const int32_t *adj;
+    const int32_t *deg;
     int n;
-    volatile uint8_t *status;                  // by original index: 0 undecided, 1 kept, 2 suppressed
-    int32_t *len;                              // live length of every candidate list (compacted round by round)
-    int *changed;                              // [2]
+    int32_t *status;                           // by original index: 0 undecided, 1 kept, 2 suppressed
+    int32_t *pending;
     NmsCounters *ctr;
-    unsigned int *qcount;                      // [2] queue fill, double buffered by round parity
-    int2 *queue;                               // (box, adj position); capacity = number of candidates
-    unsigned int *wcount;                      // [2] worklist fill (boxes still undecided after a round), same parity scheme
-    int32_t *worklist;                         // [2][n]
+    unsigned int *counts;                      // [0..1] kept frontier fill by round parity, [2..3] suppressed frontier, [4..5] queue
+    int32_t *fkept, *fsup;                     // [2][n] each
+    int2 *queue;                               // (worse box, better box); capacity = number of candidates
     const float4 *aabb, *v01, *v23;
     const float *area;
     double thr;
     int union_mode;
+    int trace;                                 // ORP_NMS_TRACE=1: block 0 prints per-round frontier sizes and phase times
 };
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(256, 4)
 nms_resolve_lazy_kernel(LazyParams P)
 {
     cg::grid_group grid = cg::this_grid();
@@ -618,94 +642,111 @@ nms_resolve_lazy_kernel(LazyParams P)
     const int lane = threadIdx.x & 31, gwarp = tid >> 5, nwarps = nth >> 5;
     const unsigned lt = (1u << lane) - 1u;
     unsigned long long c_clip = 0, c_64 = 0, c_sup = 0;
+    // boxes nobody better overlaps are kept outright: the first frontier
+    for (int r0 = blockIdx.x * blockDim.x; r0 < P.n; r0 += nth) {
+        const int r = r0 + threadIdx.x;
+        const bool k = r < P.n && P.pending[r] == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, k);
+        if (m) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&P.counts[0], (unsigned int)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (k) { P.status[r] = 1; P.fkept[base + __popc(m & lt)] = r; }
+        }
+    }
+    __threadfence();
+    grid.sync();
     int round = 0;
     while (true) {
-        int *flag = &P.changed[round & 1];
-        unsigned int *qc = &P.qcount[round & 1];
-        int local = 0;
-        // ---- phase A: round 0 visits every box, later rounds only the boxes the previous round left undecided
-        const unsigned int nsrc = round == 0 ? (unsigned int)P.n : *(volatile unsigned int *)&P.wcount[(round - 1) & 1];
-        const int32_t *src = P.worklist + (size_t)((round - 1) & 1) * P.n;
-        int32_t *dst = P.worklist + (size_t)(round & 1) * P.n;
-        for (unsigned int w = gwarp; w < nsrc; w += nwarps) {
-            const int r = round == 0 ? (int)w : src[w];
-            if (P.status[r] != 0) continue;
-            if (round == 0) {
-                // nothing is kept yet: a box without candidates is kept, every other box waits - no need to walk its list
-                if (lane == 0) {
-                    if (P.len[r] == 0) P.status[r] = 1;
-                    else dst[atomicAdd(&P.wcount[0], 1u)] = r;
-                }
-                local = 1;
-                continue;
-            }
-            const int b = P.offs[r], e = b + P.len[r];
-            bool pend = false, undec = false;
-            int outpos = b;                                  // in-place compaction: writes never pass the chunk being read
+        const int cur = round & 1, nxt = cur ^ 1;
+        const unsigned int nk = *(volatile unsigned int *)&P.counts[cur];
+        const unsigned int ns = *(volatile unsigned int *)&P.counts[2 + cur];
+        if (nk == 0 && ns == 0) break;
+        const int32_t *fk = P.fkept + (size_t)cur * P.n, *fs = P.fsup + (size_t)cur * P.n;
+        int32_t *fk_next = P.fkept + (size_t)nxt * P.n, *fs_next = P.fsup + (size_t)nxt * P.n;
+        unsigned int *qc = &P.counts[4 + cur];
+        const unsigned long long t0 = P.trace ? gtime() : 0ull;
+        // ---- phase 1
+        for (unsigned int w = gwarp; w < nk + ns; w += nwarps) {
+            const bool kept = w < nk;
+            const int j = kept ? fk[w] : fs[w - nk];
+            const int b = P.offs[j], e = b + P.deg[j];
             for (int k0 = b; k0 < e; k0 += 32) {
                 const int k = k0 + lane;
-                bool need = false, un = false;
-                int j = -1;
+                int r = -1;
+                bool act = false;
                 if (k < e) {
-                    j = P.adj[k];
-                    if (j >= 0) {
-                        const uint8_t st = P.status[j];
-                        need = (st == 1);
-                        un = (st == 0);
+                    r = P.adj[k];
+                    act = *(volatile int32_t *)&P.status[r] == 0;
+                }
+                if (kept) {
+                    const unsigned m = __ballot_sync(0xffffffffu, act);
+                    if (m) {
+                        unsigned int base = 0;
+                        if (lane == 0) base = atomicAdd(qc, (unsigned int)__popc(m));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (act) P.queue[base + __popc(m & lt)] = make_int2(r, j);
+                    }
+                } else if (act) {
+                    if (atomicSub(&P.pending[r], 1) == 1) {
+                        P.status[r] = 1;
+                        fk_next[atomicAdd(&P.counts[nxt], 1u)] = r;
                     }
                 }
-                const bool live = need || un;
-                const unsigned lm = __ballot_sync(0xffffffffu, live);
-                const int mypos = outpos + __popc(lm & lt);
-                if (live) P.adj[mypos] = j;
-                const unsigned m = __ballot_sync(0xffffffffu, need);
-                if (m) {
-                    unsigned int base = 0;
-                    if (lane == 0) base = atomicAdd(qc, (unsigned int)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (need) P.queue[base + __popc(m & lt)] = make_int2(r, mypos);
-                    pend = true;
-                }
-                undec = undec || (lm & ~m) != 0u;
-                outpos += __popc(lm);
             }
-            if (lane == 0) P.len[r] = outpos - b;
-            if (pend) local = 1;
-            else if (!undec) {
-                if (lane == 0) P.status[r] = 1;
-                local = 1;
-            }
-            if ((pend || undec) && lane == 0) dst[atomicAdd(&P.wcount[round & 1], 1u)] = r;
         }
-        if (local) *flag = 1;
         __threadfence();
         grid.sync();
-        const int any = *(volatile int *)flag;
         const unsigned int nq = *(volatile unsigned int *)qc;
-        if (tid == 0) { P.changed[(round + 1) & 1] = 0; P.qcount[(round + 1) & 1] = 0; P.wcount[(round + 1) & 1] = 0; }
-        // ---- phase B
-        for (unsigned int q = tid; q < nq; q += nth) {
-            const int2 e = P.queue[q];
-            const int r = e.x, j = P.adj[e.y];
+        const unsigned long long t1 = P.trace ? gtime() : 0ull;
+        if (tid == 0) { P.counts[cur] = 0; P.counts[2 + cur] = 0; P.counts[4 + nxt] = 0; }
+        // ---- phase 2 (the loop bound is warp-uniform: pairs the fp32 clip cannot decide are finished by the whole warp)
+        for (unsigned int q0 = (unsigned int)(tid - lane); q0 < nq; q0 += nth) {
+            const unsigned int q = q0 + lane;
+            int r = -1, j = -1, res = 0;
+            bool valid = q < nq;
             Quad A, B;
-            {
+            if (valid) {
+                const int2 e = P.queue[q];
+                r = e.x; j = e.y;
+                valid = *(volatile int32_t *)&P.status[r] == 0;    // else another pair of this round already suppressed it
+            }
+            if (valid) {
                 const float4 t0 = P.v01[r], t1 = P.v23[r];
                 A.c[0] = t0.x; A.c[1] = t0.y; A.c[2] = t0.z; A.c[3] = t0.w; A.c[4] = t1.x; A.c[5] = t1.y; A.c[6] = t1.z; A.c[7] = t1.w;
                 const float4 u0 = P.v01[j], u1 = P.v23[j];
                 B.c[0] = u0.x; B.c[1] = u0.y; B.c[2] = u0.z; B.c[3] = u0.w; B.c[4] = u1.x; B.c[5] = u1.y; B.c[6] = u1.z; B.c[7] = u1.w;
+                res = decide_fast(A, B, P.aabb[r], P.aabb[j], P.area[r] >= 0.f && P.area[j] >= 0.f, P.thr, scratch);
+                ++c_clip;
             }
-            bool used64;
-            const bool sup = decide_exact<1>(A, B, P.aabb[r], P.aabb[j], P.area[r] >= 0.f && P.area[j] >= 0.f, P.thr, P.union_mode,
-                                             used64, scratch);
-            ++c_clip;
-            c_64 += used64;
-            if (sup) { P.status[r] = 2; ++c_sup; }
-            else P.adj[e.y] = -1;
+            unsigned hard = __ballot_sync(0xffffffffu, valid && res < 0);
+            while (hard) {
+                const int src = __ffs(hard) - 1;
+                hard &= hard - 1;
+                Quad HA, HB;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    HA.c[k] = __shfl_sync(0xffffffffu, A.c[k], src);
+                    HB.c[k] = __shfl_sync(0xffffffffu, B.c[k], src);
+                }
+                const bool s = decide_fp64_warp(HA, HB, P.thr, P.union_mode, lane);
+                if (lane == src) { res = s ? 1 : 0; ++c_64; }
+            }
+            if (!valid) continue;
+            if (res) {
+                ++c_sup;
+                if (atomicExch(&P.status[r], 2) == 0) fs_next[atomicAdd(&P.counts[2 + nxt], 1u)] = r;
+            } else if (atomicSub(&P.pending[r], 1) == 1) {
+                P.status[r] = 1;
+                fk_next[atomicAdd(&P.counts[nxt], 1u)] = r;
+            }
         }
         ++round;
         __threadfence();
         grid.sync();
-        if (!any) break;
+        if (P.trace && tid == 0)
+            printf("round %d: kept %u sup %u queue %u  phase1 %.1f us  phase2 %.1f us\n", round - 1, nk, ns, nq, (t1 - t0) * 1e-3,
+                   (gtime() - t1) * 1e-3);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -729,18 +770,18 @@ __global__ void nms_export_overflow_kernel(const NmsCounters *ctr, int32_t *stat
 }
 
 __global__ void __launch_bounds__(256)
-nms_flags_kernel(const uint8_t *__restrict__ status, const int32_t *__restrict__ order,
-                 const int32_t *__restrict__ rank, int by_orig, int n, int out_order,
+nms_flags_kernel(const uint8_t *__restrict__ status, const int32_t *__restrict__ status_orig, const int32_t *__restrict__ order,
+                 const int32_t *__restrict__ rank, int n, int out_order,
                  uint8_t *__restrict__ flags, int64_t *__restrict__ vals)
 {
-    // status is indexed by rank (COMPAT32) or by original box index (EXACT64: by_orig)
+    // status is indexed by rank (COMPAT32); status_orig by original box index (EXACT64)
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     if (out_order == ORP_ORDER_SCORE_DESC) {
-        flags[k] = status[by_orig ? order[k] : k] == 1;      // k = rank, order[k] = its original index
+        flags[k] = (status_orig ? status_orig[order[k]] : (int32_t)status[k]) == 1;      // k = rank, order[k] = its original index
         vals[k] = order[k];
     } else {
-        flags[k] = status[by_orig ? k : rank[k]] == 1;
+        flags[k] = (status_orig ? status_orig[k] : (int32_t)status[rank[k]]) == 1;
         vals[k] = k;
     }
 }
@@ -792,11 +833,12 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
     uint8_t *status = S.get<uint8_t>(n), *flags = S.get<uint8_t>(n);
     int64_t *vals = S.get<int64_t>(n);
     int *changed = S.get<int>(2);
-    unsigned int *qcount = S.get<unsigned int>(4);                // [0..1] queue fill, [2..3] worklist fill
-    int32_t *worklist = lazy ? S.get<int32_t>(2 * (size_t)n) : nullptr;
+    unsigned int *qcount = S.get<unsigned int>(6);                // frontier / queue fills of the lazy resolve
+    int32_t *worklist = lazy ? S.get<int32_t>(4 * (size_t)n) : nullptr;   // kept and suppressed frontiers, [2][n] each
+    int32_t *status32 = lazy ? S.get<int32_t>(n) : nullptr, *pending = lazy ? S.get<int32_t>(n) : nullptr;
     NmsGlobal *glob = S.get<NmsGlobal>(1);
     NmsCounters *ctr = S.get<NmsCounters>(1);
-    if (!ctr || !vals || !changed || !qcount || !glob || (lazy && !worklist)) return fail(ORP_ECUDA, "orp_rnms: scratch allocation failed");
+    if (!ctr || !vals || !changed || !qcount || !glob || (lazy && (!worklist || !status32 || !pending))) return fail(ORP_ECUDA, "orp_rnms: scratch allocation failed");
 
     size_t tb1 = 0, tb2 = 0, tb3 = 0, tb4 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb1, score_key, score_key2, iota, order_r, n, 0, 32, st);
@@ -814,7 +856,11 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
     ORP_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)(n + 1), st));
     ORP_CUDA(cudaMemsetAsync(status, 0, (size_t)n, st));
     ORP_CUDA(cudaMemsetAsync(changed, 0, 2 * sizeof(int), st));
-    ORP_CUDA(cudaMemsetAsync(qcount, 0, 4 * sizeof(unsigned int), st));
+    ORP_CUDA(cudaMemsetAsync(qcount, 0, 6 * sizeof(unsigned int), st));
+    if (lazy) {
+        ORP_CUDA(cudaMemsetAsync(status32, 0, sizeof(int32_t) * (size_t)n, st));
+        ORP_CUDA(cudaMemsetAsync(pending, 0, sizeof(int32_t) * (size_t)n, st));
+    }
     {
         NmsGlobal g0;
         g0.ymin_key = 0xFFFFFFFFu; g0.maxh_bits = 0u; g0.sumh = 0.0; g0.count = 0u;
@@ -851,7 +897,7 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
                 nms_slots_kernel<<<GM, T, 0, st>>>(sweep_key2, perm, baabb, m, aabb, sg, rk, nvalid);   // sg = group, rk = box id
                 ORP_LAUNCHED();
             }
-            SweepParams P{aabb, sg, rk, v01, v23, area, rank, nvalid, glob, R, edges, indeg, cap, ctr, thr, union_mode};
+            SweepParams P{aabb, sg, rk, v01, v23, area, rank, nvalid, glob, R, edges, indeg, pending, cap, ctr, thr, union_mode};
             int grid = ceil_div(m, kSweepWarps);
             const int maxgrid = 148 * 8 * 4;
             if (grid > maxgrid) grid = maxgrid;
@@ -887,6 +933,7 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
         if (cap > all_pairs) cap = all_pairs;
         ORP_CUDA(cudaMemsetAsync(ctr, 0, sizeof(NmsCounters), st));
         ORP_CUDA(cudaMemsetAsync(indeg, 0, sizeof(int32_t) * (size_t)(n + 1), st));
+        if (lazy) ORP_CUDA(cudaMemsetAsync(pending, 0, sizeof(int32_t) * (size_t)n, st));
     }
     // the loop above leaves `edges` as the last buffer obtained from S
     int2 *edges = static_cast<int2 *>(S.ptrs[S.n - 1]);
@@ -908,11 +955,12 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
             ORP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_resolve_lazy_kernel, 256, 0));
             if (per_sm > 4) per_sm = 4;
             int grid = sms * (per_sm > 0 ? per_sm : 1);
-            int need = ceil_div(n, 8);                       // a warp per box in the scan phase
+            int need = ceil_div(n, 8);                       // a warp per frontier box
             if (grid > need) grid = need;
             // the candidate buffer is free once scattered into the CSR: it becomes the work queue; after the scatter
             // `cursor` holds every list's length
-            LazyParams LP{offs, adj, n, status, cursor, changed, ctr, qcount, edges, qcount + 2, worklist, baabb, v01, v23, area, thr, union_mode};
+            LazyParams LP{offs, adj, cursor, n, status32, pending, ctr, qcount, worklist, worklist + 2 * (size_t)n, edges,
+                          baabb, v01, v23, area, thr, union_mode, getenv("ORP_NMS_TRACE") ? 1 : 0};
             void *args[] = {&LP};
             ORP_CUDA(cudaLaunchCooperativeKernel((void *)nms_resolve_lazy_kernel, dim3(grid), dim3(256), args, 0, st));
             ORP_LAUNCHED();
@@ -937,7 +985,7 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
         ORP_LAUNCHED();
     }
     // EXACT64: status is indexed by original box index; COMPAT32: by rank
-    nms_flags_kernel<<<G, T, 0, st>>>(status, order_r, rank, lazy ? 1 : 0, n, flags_out ? ORP_ORDER_INDEX_ASC : order,
+    nms_flags_kernel<<<G, T, 0, st>>>(status, lazy ? status32 : nullptr, order_r, rank, n, flags_out ? ORP_ORDER_INDEX_ASC : order,
                                       flags_out ? flags_out : flags, vals);
     ORP_LAUNCHED();
     if (keep_out && num_out) {

@@ -186,10 +186,11 @@ nms_regs_kernel(const float4 *__restrict__ baabb, const int32_t *__restrict__ se
     }
 }
 
-// sorted registrations -> the arrays the sweep streams: AABB, (segment : strip) group, box id
+// sorted registrations -> the arrays the sweep streams: AABB and (group = segment : strip, box id, area, rank)
 __global__ void __launch_bounds__(256)
-nms_slots_kernel(const uint64_t *__restrict__ keys, const int32_t *__restrict__ vals, const float4 *__restrict__ baabb, int m,
-                 float4 *__restrict__ aabb_s, int32_t *__restrict__ grp_s, int32_t *__restrict__ bid_s, int32_t *__restrict__ nvalid)
+nms_slots_kernel(const uint64_t *__restrict__ keys, const int32_t *__restrict__ vals, const float4 *__restrict__ baabb,
+                 const float *__restrict__ area, const int32_t *__restrict__ rank, int m,
+                 float4 *__restrict__ aabb_s, int4 *__restrict__ meta_s, int32_t *__restrict__ nvalid)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= m) return;
@@ -197,8 +198,8 @@ nms_slots_kernel(const uint64_t *__restrict__ keys, const int32_t *__restrict__ 
     const bool valid = (k != ~0ull);
     const int i = vals[s];
     aabb_s[s] = baabb[i];
-    grp_s[s] = (int32_t)(k >> 32);
-    bid_s[s] = i;
+    // everything the sweep needs about the slot's box next to its AABB: no dependent gathers while walking
+    meta_s[s] = make_int4((int32_t)(k >> 32), i, __float_as_int(area[i]), rank[i]);
     const bool prev_valid = (s == 0) ? true : (keys[s - 1] != ~0ull);
     if (!valid && prev_valid) *nvalid = s;                   // first padding slot = number of registrations
     if (valid && s == m - 1) *nvalid = m;
@@ -302,10 +303,8 @@ __device__ __forceinline__ int decide_fast(const Quad &A, const Quad &B, const f
 
 struct SweepParams {
     const float4 *aabb_s;                      // per registration slot (sweep order)
-    const int32_t *grp_s, *bid_s;
+    const int4 *meta_s;                        // (group, box id, area bits, rank)
     const float4 *v01, *v23;                   // per box (original index)
-    const float *area;
-    const int32_t *rank;
     const int32_t *nvalid;
     const NmsGlobal *G;
     int R;
@@ -352,10 +351,13 @@ __device__ __forceinline__ bool frame_prune(const float *p, const float *q, floa
 // start left of i's right edge; lanes test AABBs (coalesced float4 reads of the sorted array), survivors of the area bound
 // are compacted into a per-warp shared-memory queue, filtered by the projection bounds in both boxes' frames, and emitted
 // as candidate pairs (better-ranked box, worse-ranked box) by ORIGINAL index.
-__global__ void __launch_bounds__(kSweepWarps * 32, 6)
+template <int MINB>
+__global__ void __launch_bounds__(kSweepWarps * 32, MINB)
 nms_sweep_kernel(SweepParams P)
 {
-    __shared__ int32_t q1[kSweepWarps][64];    // (registration slot) AABB + area-bound survivors
+    __shared__ int32_t q1[kSweepWarps][64];    // AABB + area-bound survivors: box id,
+    __shared__ int32_t q1r[kSweepWarps][64];   //   rank,
+    __shared__ float q1a[kSweepWarps][64];     //   area
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nv = *P.nvalid;
     const int nwarps = gridDim.x * kSweepWarps;
@@ -367,11 +369,12 @@ nms_sweep_kernel(SweepParams P)
 
     for (int i = blockIdx.x * kSweepWarps + wib; i < nv; i += nwarps) {
         const float4 ba = P.aabb_s[i];
-        const int grp_i = P.grp_s[i];
+        const int4 mi = P.meta_s[i];
+        const int grp_i = mi.x;
         const int strip_i = grp_i & 0xFFFF;
-        const int bi = P.bid_s[i];
-        const int rk_i = P.rank[bi];
-        const float area_i = P.area[bi];
+        const int bi = mi.y;
+        const int rk_i = mi.w;
+        const float area_i = __int_as_float(mi.z);
         float A[8];
         {
             const float4 t0 = P.v01[bi], t1 = P.v23[bi];
@@ -383,11 +386,13 @@ nms_sweep_kernel(SweepParams P)
             // ---- stage 0: walk the x-interval, AABB test + strip ownership + area bound -> q1
             bool hit = false;
             const int j = base + lane;
+            int4 mj = make_int4(0, 0, 0, 0);
             if (more) {
                 bool cont = false;
                 if (j < nv) {
                     const float4 bb = P.aabb_s[j];
-                    cont = (P.grp_s[j] == grp_i) && (bb.x <= ba.z);
+                    mj = P.meta_s[j];
+                    cont = (mj.x == grp_i) && (bb.x <= ba.z);
                     if (cont) {
                         ++c_swept;
                         hit = (bb.x < ba.z) && (bb.y < ba.w) && (bb.w > ba.y);
@@ -398,7 +403,7 @@ nms_sweep_kernel(SweepParams P)
                             // exact-safe area bound: inter <= min(area_i, area_j, |AABB_i ^ AABB_j|)
                             const float iw = fminf(ba.z, bb.z) - fmaxf(ba.x, bb.x);
                             const float ih = fminf(ba.w, bb.w) - fmaxf(ba.y, bb.y);
-                            const float area_j = P.area[P.bid_s[j]];
+                            const float area_j = __int_as_float(mj.z);
                             const float imax = fminf(fminf(area_i, area_j), iw * ih);
                             if (imax * (1.f + thrf) < 0.999f * thrf * (area_i + area_j) && imax > 0.f) hit = false;
                         }
@@ -407,17 +412,21 @@ nms_sweep_kernel(SweepParams P)
                 more = __all_sync(0xffffffffu, cont);
             }
             const unsigned hm = __ballot_sync(0xffffffffu, hit);
-            if (hit) q1[wib][n1 + __popc(hm & lt)] = P.bid_s[j];
+            if (hit) {
+                const int at = n1 + __popc(hm & lt);
+                q1[wib][at] = mj.y; q1r[wib][at] = mj.w; q1a[wib][at] = __int_as_float(mj.z);
+            }
             n1 += __popc(hm);
             __syncwarp();
             // ---- stage 1: projection bounds in both frames -> candidate pairs
             while (n1 >= 32 || (!more && n1 > 0)) {
                 const int take = n1 < 32 ? n1 : 32;
                 bool pass = false;
-                int bj = 0;
+                int bj = 0, rk_j = 0;
                 if (lane < take) {
                     bj = q1[wib][n1 - take + lane];
-                    const float area_j = P.area[bj];
+                    rk_j = q1r[wib][n1 - take + lane];
+                    const float area_j = q1a[wib][n1 - take + lane];
                     pass = true;
                     if (area_i >= 0.f && area_j >= 0.f) {             // both convex: bounds are valid
                         float b[8];
@@ -435,7 +444,7 @@ nms_sweep_kernel(SweepParams P)
                     basep = __shfl_sync(0xffffffffu, basep, 0);
                     if (pass) {
                         const unsigned long long pos = basep + __popc(pm & lt);
-                        const bool i_worse = rk_i > P.rank[bj];
+                        const bool i_worse = rk_i > rk_j;
                         const int lo = i_worse ? bi : bj, hi = i_worse ? bj : bi;
                         if (pos < P.edge_cap) {
                             P.edges[pos] = make_int2(hi, lo);
@@ -671,27 +680,35 @@ nms_resolve_lazy_kernel(LazyParams P)
             const bool kept = w < nk;
             const int j = kept ? fk[w] : fs[w - nk];
             const int b = P.offs[j], e = b + P.deg[j];
-            for (int k0 = b; k0 < e; k0 += 32) {
-                const int k = k0 + lane;
-                int r = -1;
-                bool act = false;
-                if (k < e) {
-                    r = P.adj[k];
-                    act = *(volatile int32_t *)&P.status[r] == 0;
+            // four chunks of the list in flight per warp: the walk is a chain of dependent loads (entry -> status -> atomic)
+            for (int k0 = b; k0 < e; k0 += 128) {
+                int r[4];
+                bool act[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + 32 * u + lane;
+                    r[u] = k < e ? P.adj[k] : -1;
                 }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) act[u] = r[u] >= 0 && *(volatile int32_t *)&P.status[r[u]] == 0;
                 if (kept) {
-                    const unsigned m = __ballot_sync(0xffffffffu, act);
-                    if (m) {
-                        unsigned int base = 0;
-                        if (lane == 0) base = atomicAdd(qc, (unsigned int)__popc(m));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (act) P.queue[base + __popc(m & lt)] = make_int2(r, j);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const unsigned m = __ballot_sync(0xffffffffu, act[u]);
+                        if (m) {
+                            unsigned int base = 0;
+                            if (lane == 0) base = atomicAdd(qc, (unsigned int)__popc(m));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            if (act[u]) P.queue[base + __popc(m & lt)] = make_int2(r[u], j);
+                        }
                     }
-                } else if (act) {
-                    if (atomicSub(&P.pending[r], 1) == 1) {
-                        P.status[r] = 1;
-                        fk_next[atomicAdd(&P.counts[nxt], 1u)] = r;
-                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (act[u] && atomicSub(&P.pending[r[u]], 1) == 1) {
+                            P.status[r[u]] = 1;
+                            fk_next[atomicAdd(&P.counts[nxt], 1u)] = r[u];
+                        }
                 }
             }
         }
@@ -828,6 +845,7 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
     int32_t *rank = S.get<int32_t>(n);
     float4 *aabb = S.get<float4>(m), *v01 = S.get<float4>(n), *v23 = S.get<float4>(n), *baabb = S.get<float4>(n);
     int32_t *rk = S.get<int32_t>(m), *sg = S.get<int32_t>(m), *nvalid = S.get<int32_t>(1);
+    int4 *meta_s = lazy ? S.get<int4>(m) : nullptr;
     float *area = S.get<float>(n);
     int32_t *indeg = S.get<int32_t>(n + 1), *offs = S.get<int32_t>(n + 1), *cursor = S.get<int32_t>(n + 1);
     uint8_t *status = S.get<uint8_t>(n), *flags = S.get<uint8_t>(n);
@@ -838,7 +856,7 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
     int32_t *status32 = lazy ? S.get<int32_t>(n) : nullptr, *pending = lazy ? S.get<int32_t>(n) : nullptr;
     NmsGlobal *glob = S.get<NmsGlobal>(1);
     NmsCounters *ctr = S.get<NmsCounters>(1);
-    if (!ctr || !vals || !changed || !qcount || !glob || (lazy && (!worklist || !status32 || !pending))) return fail(ORP_ECUDA, "orp_rnms: scratch allocation failed");
+    if (!ctr || !vals || !changed || !qcount || !glob || (lazy && (!worklist || !status32 || !pending || !meta_s))) return fail(ORP_ECUDA, "orp_rnms: scratch allocation failed");
 
     size_t tb1 = 0, tb2 = 0, tb3 = 0, tb4 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb1, score_key, score_key2, iota, order_r, n, 0, 32, st);
@@ -894,10 +912,10 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
                 ORP_LAUNCHED();
                 ORP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb2, sweep_key, sweep_key2, iota, perm, m, 0, sweep_bits, st));
                 count_launches((sweep_bits + 7) / 8);
-                nms_slots_kernel<<<GM, T, 0, st>>>(sweep_key2, perm, baabb, m, aabb, sg, rk, nvalid);   // sg = group, rk = box id
+                nms_slots_kernel<<<GM, T, 0, st>>>(sweep_key2, perm, baabb, area, rank, m, aabb, meta_s, nvalid);
                 ORP_LAUNCHED();
             }
-            SweepParams P{aabb, sg, rk, v01, v23, area, rank, nvalid, glob, R, edges, indeg, pending, cap, ctr, thr, union_mode};
+            SweepParams P{aabb, meta_s, v01, v23, nvalid, glob, R, edges, indeg, pending, cap, ctr, thr, union_mode};
             int grid = ceil_div(m, kSweepWarps);
             const int maxgrid = 148 * 8 * 4;
             if (grid > maxgrid) grid = maxgrid;
@@ -905,7 +923,10 @@ int run_nms(const float *dets, const int32_t *segments, int n, double thr, int i
                 if (!g_ev[0]) { ORP_CUDA(cudaEventCreate(&g_ev[0])); ORP_CUDA(cudaEventCreate(&g_ev[1])); }
                 ORP_CUDA(cudaEventRecord(g_ev[0], st));
             }
-            nms_sweep_kernel<<<grid, kSweepWarps * 32, 0, st>>>(P);
+            static const int minb = getenv("ORP_NMS_SWEEP_MINB") ? atoi(getenv("ORP_NMS_SWEEP_MINB")) : 4;
+            if (minb == 6) nms_sweep_kernel<6><<<grid, kSweepWarps * 32, 0, st>>>(P);
+            else if (minb == 3) nms_sweep_kernel<3><<<grid, kSweepWarps * 32, 0, st>>>(P);
+            else nms_sweep_kernel<4><<<grid, kSweepWarps * 32, 0, st>>>(P);
             ORP_LAUNCHED();
             if (g_timing) ORP_CUDA(cudaEventRecord(g_ev[1], st));
         } else {

@@ -101,6 +101,7 @@ struct alignas(64) TcParams {
     int res_mma;                              // residual added by the tensor core: extra K blocks  R[128x64] * I[64x64]
     int epi_split;                            // epilogue-bound layers: the two epilogue warpgroups work on alternate tiles (one per accumulator buffer)
     int gn_fused;                             // GroupNorm statistics accumulated in the TMA epilogue (Cout == 256)
+    int dcat;                                 // deformable split mode: one stage = sampled x_hi | x_lo | w_hi | w_lo of a K block
     int stem;                                 // producers build conv1's 7x7/2 im2col rows from the NCHW fp32 image
     int s2d_stem;                             // conv1 in space-to-depth form (host bookkeeping: 147 useful K of 256)
     int split;                                // f16x3 mode: fp16 (hi, lo) operand pairs, three MMA terms per K block
@@ -270,10 +271,13 @@ struct Ring {
 //                             error grows linearly with the step count, 6e-6 of max at 432 steps); while only the 2^-11
 //                             times smaller cross terms have been added the accumulator's ulp - hence that loss - is 2^-11
 //                             times smaller too, so the loss of a tile is that of K/16 steps instead of 3K/16.
-//   split, deformable:        (tap, channel block, term): the producers sample once and fill three stages back to back.
+//   split, deformable:        tap-major, one stage per (tap, channel block) carrying both halves of both operands (dcat): the
+//                             producers sample once and hand the K block over once - with one stage per term they could
+//                             only start the next gather after the THIRD stage of a block had been freed, which exposed
+//                             two thirds of the gather time.
 struct KIter {
     int tap, term, cb = 0, phase = 0;
-    int tap0, taps, cbn, mode;                             // taps [tap0, taps); mode 0: bf16, 1: split TMA, 2: split deformable
+    int tap0, taps, cbn, mode;                             // taps [tap0, taps); mode 0: one stage per K block, 1: split TMA (a stage per term)
     __device__ KIter(int taps_, int cbn_, int mode_, int tap0_ = 0) : tap0(tap0_), taps(taps_), cbn(cbn_), mode(mode_)
     {
         tap = tap0;
@@ -282,7 +286,6 @@ struct KIter {
     __device__ void next()
     {
         if (mode == 0) { if (++cb == cbn) { cb = 0; ++tap; } }
-        else if (mode == 2) { if (++term == 3) { term = 0; if (++cb == cbn) { cb = 0; ++tap; } } }
         else if (phase == 0) {
             if (++cb == cbn) { cb = 0; if (++term == 3) { term = 1; if (++tap == taps) { tap = tap0; term = 0; phase = 1; } } }
         } else { if (++cb == cbn) { cb = 0; ++tap; } }
@@ -340,7 +343,8 @@ __device__ unsigned int g_f16_overflow = 0;
 
 // ----------------------------------------------------------------------------------------------- kernel
 // BN: accumulator width (32..256).  OUT_F32: fp32 output (head predictions) instead of bf16.
-// DEFORM: A operand produced by warps 6-9 (bilinear gather) instead of TMA.
+constexpr int kStemPatchBytes = 24576;             // conv1's input patch in dynamic shared memory (5632 floats used)
+// DEFORM: A operand produced by warps 6-13 (bilinear gather) instead of TMA.
 template <int BN, bool OUT_F32, bool DEFORM>
 __global__ void __launch_bounds__(DEFORM ? 448 : 320, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
@@ -355,11 +359,13 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kBBytes = BN * kBK * 2;
     // b_resident: [B slab: kblocks x kBBytes] then A-only stages; otherwise every stage carries A | B
-    const int kStageBytes = P.ncat ? (P.b_resident ? 2 * kABytes : 2 * kABytes + 2 * kBBytes)
+    const int kStageBytes = (P.ncat || P.dcat) ? (P.b_resident ? 2 * kABytes : 2 * kABytes + 2 * kBBytes)
                                    : (P.b_resident ? kABytes : kABytes + kBBytes);
     const int kblocks_all = P.KH * P.KW * P.cin_blocks * (P.split ? 2 : 1);   // weight K blocks (hi and lo halves in split mode)
     uint8_t *ident = smem;                             // [8 KiB] identity block when res_mma
     if (P.res_mma) smem += 8192;
+    float *s_patch = reinterpret_cast<float *>(smem);  // [24 KiB] conv1's input patch (stem transform only)
+    if (DEFORM && P.stem) smem += kStemPatchBytes;
     uint8_t *bres = smem;
     if (P.b_resident) smem += (size_t)kblocks_all * kBBytes;
     constexpr int HC = BN < 64 ? BN : 64;              // columns staged per epilogue pass
@@ -389,7 +395,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     if (warp == 1) {
         if (elect_one()) {
             for (int s = 0; s < stages; ++s) {
-                mbar_init(&full[s], DEFORM ? 1 + 256 : 1);
+                mbar_init(&full[s], DEFORM ? 1 + 8 : 1);          // TMA expect_tx arrival (+ one arrival per producer warp)
                 mbar_init(&empty[s], 1);
             }
             for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], (kWG == 2 && P.epi_split) ? 4 : kEpiWarps); }
@@ -405,7 +411,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int taps_per = (P.KH * P.KW) / (P.ksplit > 1 ? P.ksplit : 1);              // taps of one K split
-    const int kblocks = taps_per * P.cin_blocks * ((P.split && !P.ncat) ? 3 : 1);     // main-loop K blocks (stages) per tile
+    const int kblocks = taps_per * P.cin_blocks * ((P.split && !P.ncat && !P.dcat) ? 3 : 1);     // main-loop K blocks (stages) per tile
     // Programmatic dependent launch: the next kernel in the stream may start its CTAs (barrier init, TMEM allocation,
     // descriptor prefetch - the code above) on SMs this grid has already left; nothing above touches global memory,
     // and everything below (loads AND stores) comes after the wait for the preceding grid to complete and flush.
@@ -432,17 +438,20 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                 const Problem &pr = P.prob[pi];
                 const int w0 = wb * pr.BW * P.stride - P.pad, h0 = hb * pr.BH * P.stride - P.pad, i0 = ib * pr.BI;
                 const int tap_lo = ksplit_of(P, tile) * taps_per;
-                KIter it(tap_lo + taps_per, P.cin_blocks, (P.split && !P.ncat) ? (DEFORM ? 2 : 1) : 0, tap_lo);
+                KIter it(tap_lo + taps_per, P.cin_blocks, (P.split && !P.ncat && !P.dcat) ? 1 : 0, tap_lo);
                 for (int j = 0; j < kblocks; ++j, it.next()) {
                     const int kh = it.tap / P.KW, kw = it.tap - kh * P.KW;
                     mbar_wait(&empty[r.stage], r.phase ^ 1);
                     uint8_t *sa = smem + (size_t)r.stage * kStageBytes;
                     const int wblk = ((it.tap * P.cin_blocks + it.cb) * wterms) * kBK;      // K offset of the (hi, lo) weight blocks
-                    if (P.ncat) {
-                        // one stage = x_hi tile | x_lo tile | w_hi block | w_lo block of this (tap, channel block)
-                        mbar_expect_tx(&full[r.stage], P.b_resident ? 2 * kABytes : 2 * kABytes + 2 * kBBytes);
-                        tma_load_5d(sa, &P.tmA[pi], &full[r.stage], it.cb * kBK, 0, w0 + kw, h0 + kh, i0);
-                        tma_load_5d(sa + kABytes, &P.tmA[pi], &full[r.stage], it.cb * kBK, 1, w0 + kw, h0 + kh, i0);
+                    if (P.ncat || P.dcat) {
+                        // one stage = x_hi tile | x_lo tile | w_hi block | w_lo block of this (tap, channel block); the
+                        // deformable variant's x halves come from the producer warps
+                        mbar_expect_tx(&full[r.stage], (DEFORM ? 0 : 2 * kABytes) + (P.b_resident ? 0 : 2 * kBBytes));
+                        if (!DEFORM) {
+                            tma_load_5d(sa, &P.tmA[pi], &full[r.stage], it.cb * kBK, 0, w0 + kw, h0 + kh, i0);
+                            tma_load_5d(sa + kABytes, &P.tmA[pi], &full[r.stage], it.cb * kBK, 1, w0 + kw, h0 + kh, i0);
+                        }
                         if (!P.b_resident) {
                             tma_load_2d(sa + 2 * kABytes, &P.tmB, &full[r.stage], wblk, nt * BN);
                             tma_load_2d(sa + 2 * kABytes + kBBytes, &P.tmB, &full[r.stage], wblk + kBK, nt * BN);
@@ -492,7 +501,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
             const uint32_t accw = P.ncat ? 2u * BN : (uint32_t)BN;          // TMEM columns of one accumulator buffer
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * accw;
             const int tap_lo = ksplit_of(P, tile) * taps_per;
-            KIter it(tap_lo + taps_per, P.cin_blocks, (P.split && !P.ncat) ? (DEFORM ? 2 : 1) : 0, tap_lo);   // same walk as the producer
+            KIter it(tap_lo + taps_per, P.cin_blocks, (P.split && !P.ncat && !P.dcat) ? 1 : 0, tap_lo);   // same walk as the producer
             for (int kb = 0; kb < kblocks; ++kb, it.next()) {
                 mbar_wait(&full[r.stage], r.phase);
                 tcgen05_fence_after();
@@ -508,6 +517,15 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                         for (int k = 0; k < kBK / 16; ++k) {
                             umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc2, (kb | k) ? 1u : 0u);        // x_hi * [w_hi | w_lo]
                             umma_bf16(d_tmem + (uint32_t)BN, dl + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);          // x_lo * w_hi -> cross columns
+                        }
+                    } else if (P.dcat) {
+                        const uint64_t dl = make_desc_sw128(sa + kABytes);
+                        const uint64_t dbh = make_desc_sw128(sa + 2 * kABytes), dbl = make_desc_sw128(sa + 2 * kABytes + kBBytes);
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k) {
+                            umma_bf16(d_tmem, dl + (uint64_t)(k * 2), dbh + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);   // x_lo * w_hi
+                            umma_bf16(d_tmem, da + (uint64_t)(k * 2), dbl + (uint64_t)(k * 2), idesc, 1u);                   // x_hi * w_lo
+                            umma_bf16(d_tmem, da + (uint64_t)(k * 2), dbh + (uint64_t)(k * 2), idesc, 1u);                   // x_hi * w_hi
                         }
                     } else {
                         const uint64_t db = make_desc_sw128(P.b_resident ? smem_u32(bres + (size_t)slab * kBBytes) : sa + kABytes);
@@ -870,7 +888,6 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
             // k = (kh*7 + kw)*3 + c.  Per tile the input patch ((2*BH+5) x (2*BW+5) pixels x 3 channels per image
             // of the tile) is staged once in shared memory with coalesced loads of the NCHW fp32 image
             // (pr.offset); the three 64-wide K blocks of A rows are then built from shared memory.
-            __shared__ float s_patch[5632];
             __shared__ __align__(16) int s_koff[192];                                      // k -> offset inside the patch (-1: k >= 147)
             {
                 const Problem &p0 = P.prob[0];
@@ -936,7 +953,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                         *reinterpret_cast<uint4 *>(sa + (size_t)row * 128 + ((c16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive(&full[r.stage]);
+                    __syncwarp();
+                    if ((pt & 31) == 0) mbar_arrive(&full[r.stage]);
                     r.next();
                 }
             }
@@ -1024,12 +1042,13 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             *reinterpret_cast<uint4 *>(sa + (size_t)row * 128 + ((c16 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy (UMMA reads smem)
-                        mbar_arrive(&full[r.stage]);
+                        __syncwarp();                                                   // every lane has fenced its own stores
+                        if ((pt & 31) == 0) mbar_arrive(&full[r.stage]);
                         r.next();
                     } else {
                         // split mode: every corner is read as its (hi, lo) fp16 pair, the sample is formed in fp32 exactly as
-                        // the reference does (deform_conv_cuda_kernel.cu:84-115), split again, and fills the three stages of
-                        // this channel block: hi (x w_hi), lo (x w_hi), hi (x w_lo)
+                        // the reference does (deform_conv_cuda_kernel.cu:84-115), split again, and written as the x_hi and
+                        // x_lo tiles of this K block's stage
                         const __half *xh = reinterpret_cast<const __half *>(pr.x);
                         uint32_t phi[4][4], plo[4][4];
 #pragma unroll
@@ -1072,19 +1091,19 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                                 }
                             }
                         }
-#pragma unroll 1
-                        for (int term = 0; term < 3; ++term) {
+                        {
                             mbar_wait(&empty[r.stage], r.phase ^ 1);
                             uint8_t *sa = smem + (size_t)r.stage * kStageBytes;
 #pragma unroll
                             for (int it = 0; it < 4; ++it) {
                                 const int item = pt + it * 256, row = item >> 3, c16 = item & 7;
-                                const uint4 o = (term == 1) ? make_uint4(plo[it][0], plo[it][1], plo[it][2], plo[it][3])
-                                                            : make_uint4(phi[it][0], phi[it][1], phi[it][2], phi[it][3]);
-                                *reinterpret_cast<uint4 *>(sa + (size_t)row * 128 + ((c16 ^ (row & 7)) << 4)) = o;
+                                const size_t at = (size_t)row * 128 + ((c16 ^ (row & 7)) << 4);
+                                *reinterpret_cast<uint4 *>(sa + at) = make_uint4(phi[it][0], phi[it][1], phi[it][2], phi[it][3]);
+                                *reinterpret_cast<uint4 *>(sa + kABytes + at) = make_uint4(plo[it][0], plo[it][1], plo[it][2], plo[it][3]);
                             }
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            mbar_arrive(&full[r.stage]);
+                            __syncwarp();
+                            if ((pt & 31) == 0) mbar_arrive(&full[r.stage]);
                             r.next();
                         }
                     }
@@ -1132,7 +1151,7 @@ thread_local TcTrace g_tc_trace[kEvPool];
 template <int BN, bool OUT_F32, bool DEFORM>
 int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st, int staging_bytes)
 {
-    const size_t stage_b = P.ncat ? (P.b_resident ? 2 * kABytes : 2 * kABytes + 2 * BN * kBK * 2)
+    const size_t stage_b = (P.ncat || P.dcat) ? (P.b_resident ? 2 * kABytes : 2 * kABytes + 2 * BN * kBK * 2)
                                   : (P.b_resident ? kABytes : kABytes + BN * kBK * 2);
     const size_t smem = 1024 + (size_t)stages * stage_b + (size_t)staging_bytes;
     auto kern = conv_tc_kernel<BN, OUT_F32, DEFORM>;
@@ -1494,6 +1513,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     P.epi_merge = (split && P.tma_epi && (mem_bound || stem == 2) && !getenv("ORP_TC_NO_MERGE")) ? 1 : 0;
     // terms concatenated along N for narrow layers (kernel header); the residual / deformable / fp32-output variants keep
     // the K-concatenated walk
+    P.dcat = (split && deform && stem != 1) ? 1 : 0;
     P.ncat = (split && P.tma_epi && BN <= 128 && !deform && !any_res && stem != 1 && !getenv("ORP_TC_NO_NCAT")) ? 1 : 0;
     // epilogue-bound layers (at most 6 K blocks per tile incl. the residual's; measured: 7-15 lose a little to the
     // smaller staging/stage budget): independent epilogue warpgroups
@@ -1558,13 +1578,13 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
     // stages they are given up in order of least value: the second epilogue group, the second staging slot, the resident slab.
     int stage_bytes = 0, bres_bytes = 0, staging = 0, stages = 0;
     for (;;) {
-        stage_bytes = P.ncat ? (P.b_resident ? 2 * kABytes : 2 * kABytes + 2 * BN * kBK * 2)
-                             : (P.b_resident ? kABytes : kABytes + BN * kBK * 2);
-        bres_bytes = (P.b_resident ? KH * KW * T * P.cin_blocks * BN * kBK * 2 : 0) + (P.res_mma ? 8192 : 0);
+        stage_bytes = (P.ncat || P.dcat) ? (P.b_resident ? 2 * kABytes : 2 * kABytes + 2 * BN * kBK * 2)
+                                         : (P.b_resident ? kABytes : kABytes + BN * kBK * 2);
+        bres_bytes = (P.b_resident ? KH * KW * T * P.cin_blocks * BN * kBK * 2 : 0) + (P.res_mma ? 8192 : 0) + (stem == 1 ? kStemPatchBytes : 0);
         const int hc = BN < 64 ? BN : 64;
         staging = out_f32 ? 0 : 128 * (hc * 2 + 16);
         if (P.tma_epi) staging = P.epi_bufs * (P.epi_merge ? 32768 : 16384) * (P.epi_split ? 2 : 1);
-        stages = (int)((227 * 1024 - 4096 - 1024 - staging - bres_bytes) / stage_bytes);
+        stages = (int)((227 * 1024 - (deform || stem == 1 ? 12288 : 4096) - 1024 - staging - bres_bytes) / stage_bytes);   // static shared memory of the variant
         if (stages >= 3) break;
         if (P.epi_split) { P.epi_split = 0; P.epi_bufs = mem_bound ? 2 : 1; continue; }
         if (P.epi_bufs == 2) { P.epi_bufs = 1; continue; }

@@ -879,6 +879,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
         // the 4 corners (every load instruction covers whole 128-byte lines), blend in fp32, round to bf16 and
         // store to the stage in the 128-byte-swizzled K-major layout the MMA expects.
         __shared__ float4 s_w[2][128];
+        __shared__ uint2 s_wh[2][128];                     // the same four weights as fp16 (split mode: blend of the lo halves)
         __shared__ int4 s_o[2][128];
         const int pt = threadIdx.x - 192;                  // 0..255
         Ring r(stages);
@@ -1002,6 +1003,10 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                     }
                     s_w[tb][pt] = wv;
                     s_o[tb][pt] = ov;
+                    if (P.split) {
+                        const __half2 w01 = __floats2half2_rn(wv.x, wv.y), w23 = __floats2half2_rn(wv.z, wv.w);
+                        s_wh[tb][pt] = make_uint2(*reinterpret_cast<const uint32_t *>(&w01), *reinterpret_cast<const uint32_t *>(&w23));
+                    }
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 for (int cb = 0; cb < P.cin_blocks; ++cb) {
@@ -1070,22 +1075,28 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             for (int i1 = 0; i1 < 2; ++i1) {
                                 const int it = i2 * 2 + i1, item = pt + it * 256, row = item >> 3;
                                 const float4 wv = s_w[tb][row];
-                                const float wc[4] = {wv.x, wv.y, wv.z, wv.w};
+                                const uint2 wh = s_wh[tb][row];
+                                const float2 wc[4] = {make_float2(wv.x, wv.x), make_float2(wv.y, wv.y), make_float2(wv.z, wv.z), make_float2(wv.w, wv.w)};
+                                const __half2 wl[4] = {__low2half2(*reinterpret_cast<const __half2 *>(&wh.x)), __high2half2(*reinterpret_cast<const __half2 *>(&wh.x)),
+                                                       __low2half2(*reinterpret_cast<const __half2 *>(&wh.y)), __high2half2(*reinterpret_cast<const __half2 *>(&wh.y))};
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    float vx = 0.f, vy = 0.f;
+                                    // hi halves: fp32, two channels per packed FMA; lo halves (<= 2^-11 of the value): blended in
+                                    // half2 arithmetic with fp16 weights - an error of 2^-11 on a 2^-11 term
+                                    float2 acc = make_float2(0.f, 0.f);
+                                    __half2 accl = __float2half2_rn(0.f);
 #pragma unroll
                                     for (int c = 0; c < 4; ++c) {
                                         const uint32_t uh = reinterpret_cast<const uint32_t *>(&u[i1][c][0])[k];
                                         const uint32_t ul = reinterpret_cast<const uint32_t *>(&u[i1][c][1])[k];
-                                        const float2 fh = __half22float2(*reinterpret_cast<const __half2 *>(&uh));
-                                        const float2 fl = __half22float2(*reinterpret_cast<const __half2 *>(&ul));
-                                        vx = fmaf(wc[c], fh.x + fl.x, vx);      // hi + lo is exact in fp32
-                                        vy = fmaf(wc[c], fh.y + fl.y, vy);
+                                        acc = __ffma2_rn(wc[c], __half22float2(*reinterpret_cast<const __half2 *>(&uh)), acc);
+                                        accl = __hfma2(wl[c], *reinterpret_cast<const __half2 *>(&ul), accl);
                                     }
-                                    const __half2 h2 = __floats2half2_rn(vx, vy);
+                                    acc = __fadd2_rn(acc, __half22float2(accl));
+                                    const __half2 h2 = __floats2half2_rn(acc.x, acc.y);
                                     const float2 hf = __half22float2(h2);
-                                    const __half2 l2 = __floats2half2_rn(vx - hf.x, vy - hf.y);
+                                    const float2 rem = __fadd2_rn(acc, make_float2(-hf.x, -hf.y));
+                                    const __half2 l2 = __floats2half2_rn(rem.x, rem.y);
                                     phi[it][k] = *reinterpret_cast<const uint32_t *>(&h2);
                                     plo[it][k] = *reinterpret_cast<const uint32_t *>(&l2);
                                 }
@@ -1584,7 +1595,7 @@ static int conv2d_bf16_impl(int nprob, const orp_tc_problem *probs, const void *
         const int hc = BN < 64 ? BN : 64;
         staging = out_f32 ? 0 : 128 * (hc * 2 + 16);
         if (P.tma_epi) staging = P.epi_bufs * (P.epi_merge ? 32768 : 16384) * (P.epi_split ? 2 : 1);
-        stages = (int)((227 * 1024 - (deform || stem == 1 ? 12288 : 4096) - 1024 - staging - bres_bytes) / stage_bytes);   // static shared memory of the variant
+        stages = (int)((227 * 1024 - (deform || stem == 1 ? 14336 : 4096) - 1024 - staging - bres_bytes) / stage_bytes);   // static shared memory of the variant
         if (stages >= 3) break;
         if (P.epi_split) { P.epi_split = 0; P.epi_bufs = mem_bound ? 2 : 1; continue; }
         if (P.epi_bufs == 2) { P.epi_bufs = 1; continue; }

@@ -344,9 +344,12 @@ __device__ unsigned int g_f16_overflow = 0;
 // ----------------------------------------------------------------------------------------------- kernel
 // BN: accumulator width (32..256).  OUT_F32: fp32 output (head predictions) instead of bf16.
 constexpr int kStemPatchBytes = 24576;             // conv1's input patch in dynamic shared memory (5632 floats used)
-// DEFORM: A operand produced by warps 6-13 (bilinear gather) instead of TMA.
+constexpr int kDP = 256;                           // deformable A-operand producer threads (warps 6 .. 6 + kDP/32 - 1)
+constexpr int kDItems = 1024 / kDP;                // (pixel row, 8-channel chunk) items of one 128 x 64 A block per thread
+constexpr int kDRound = kDItems / 2;               // items gathered together (two rounds per K block)
+// DEFORM: A operand produced by the warps from 6 on (bilinear gather) instead of TMA.
 template <int BN, bool OUT_F32, bool DEFORM>
-__global__ void __launch_bounds__(DEFORM ? 448 : 320, 1)
+__global__ void __launch_bounds__(DEFORM ? 192 + kDP : 320, 1)
 conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
 {
     // warp roles.  plain: 0 TMA | 1 MMA | 2-9 epilogue (two warps per TMEM lane quarter, splitting the columns).
@@ -395,7 +398,7 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
     if (warp == 1) {
         if (elect_one()) {
             for (int s = 0; s < stages; ++s) {
-                mbar_init(&full[s], DEFORM ? 1 + 8 : 1);          // TMA expect_tx arrival (+ one arrival per producer warp)
+                mbar_init(&full[s], DEFORM ? 1 + (P.stem ? 8 : kDP / 32) : 1);          // TMA expect_tx arrival (+ one arrival per producer warp)
                 mbar_init(&empty[s], 1);
             }
             for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], (kWG == 2 && P.epi_split) ? 4 : kEpiWarps); }
@@ -881,10 +884,12 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
         __shared__ float4 s_w[2][128];
         __shared__ uint2 s_wh[2][128];                     // the same four weights as fp16 (split mode: blend of the lo halves)
         __shared__ int4 s_o[2][128];
-        const int pt = threadIdx.x - 192;                  // 0..255
+        const int pt = threadIdx.x - 192;                  // 0..kDP-1 (the stem transform uses the first 256)
         Ring r(stages);
         int tb = 0;
-        if (P.stem) {
+        if (P.stem && pt >= 256) {
+            // conv1's operand is built from a shared-memory patch: 8 warps are plenty
+        } else if (P.stem) {
             // conv1 (resnet.py:495, 7x7 stride 2 pad 3, 3 input channels) as a GEMM with K = 192 (147 used),
             // k = (kh*7 + kw)*3 + c.  Per tile the input patch ((2*BH+5) x (2*BW+5) pixels x 3 channels per image
             // of the tile) is staged once in shared memory with coalesced loads of the NCHW fp32 image
@@ -1008,15 +1013,15 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                         s_wh[tb][pt] = make_uint2(*reinterpret_cast<const uint32_t *>(&w01), *reinterpret_cast<const uint32_t *>(&w23));
                     }
                 }
-                asm volatile("bar.sync 2, 256;" ::: "memory");
+                asm volatile("bar.sync 2, %0;" ::"n"(kDP) : "memory");
                 for (int cb = 0; cb < P.cin_blocks; ++cb) {
                     if (!P.split) {
                         mbar_wait(&empty[r.stage], r.phase ^ 1);
                         uint8_t *sa = smem + (size_t)r.stage * kStageBytes;
-                        uint4 u[4][4];
+                        uint4 u[kDItems][4];
 #pragma unroll
-                        for (int it = 0; it < 4; ++it) {
-                            const int item = pt + it * 256, row = item >> 3, c16 = item & 7;
+                        for (int it = 0; it < kDItems; ++it) {
+                            const int item = pt + it * kDP, row = item >> 3, c16 = item & 7;
                             const int4 ov = s_o[tb][row];
                             const int co = cb * kBK + c16 * 8;
                             u[it][0] = *reinterpret_cast<const uint4 *>(pr.x + ov.x + co);
@@ -1025,8 +1030,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             u[it][3] = *reinterpret_cast<const uint4 *>(pr.x + ov.w + co);
                         }
 #pragma unroll
-                        for (int it = 0; it < 4; ++it) {
-                            const int item = pt + it * 256, row = item >> 3, c16 = item & 7;
+                        for (int it = 0; it < kDItems; ++it) {
+                            const int item = pt + it * kDP, row = item >> 3, c16 = item & 7;
                             const float4 wv = s_w[tb][row];
                             const uint32_t *a1 = reinterpret_cast<const uint32_t *>(&u[it][0]);
                             const uint32_t *a2 = reinterpret_cast<const uint32_t *>(&u[it][1]);
@@ -1055,13 +1060,13 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                         // the reference does (deform_conv_cuda_kernel.cu:84-115), split again, and written as the x_hi and
                         // x_lo tiles of this K block's stage
                         const __half *xh = reinterpret_cast<const __half *>(pr.x);
-                        uint32_t phi[4][4], plo[4][4];
+                        uint32_t phi[kDItems][4], plo[kDItems][4];
 #pragma unroll
                         for (int i2 = 0; i2 < 2; ++i2) {
-                            uint4 u[2][4][2];
+                            uint4 u[kDRound][4][2];
 #pragma unroll
-                            for (int i1 = 0; i1 < 2; ++i1) {
-                                const int item = pt + (i2 * 2 + i1) * 256, row = item >> 3, c16 = item & 7;
+                            for (int i1 = 0; i1 < kDRound; ++i1) {
+                                const int item = pt + (i2 * kDRound + i1) * kDP, row = item >> 3, c16 = item & 7;
                                 const int4 ov = s_o[tb][row];
                                 const int co = cb * kBK + c16 * 8;
                                 const int oo[4] = {ov.x, ov.y, ov.z, ov.w};
@@ -1072,8 +1077,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                                 }
                             }
 #pragma unroll
-                            for (int i1 = 0; i1 < 2; ++i1) {
-                                const int it = i2 * 2 + i1, item = pt + it * 256, row = item >> 3;
+                            for (int i1 = 0; i1 < kDRound; ++i1) {
+                                const int it = i2 * kDRound + i1, item = pt + it * kDP, row = item >> 3;
                                 const float4 wv = s_w[tb][row];
                                 const uint2 wh = s_wh[tb][row];
                                 const float2 wc[4] = {make_float2(wv.x, wv.x), make_float2(wv.y, wv.y), make_float2(wv.z, wv.z), make_float2(wv.w, wv.w)};
@@ -1106,8 +1111,8 @@ conv_tc_kernel(const __grid_constant__ TcParams P, int stages)
                             mbar_wait(&empty[r.stage], r.phase ^ 1);
                             uint8_t *sa = smem + (size_t)r.stage * kStageBytes;
 #pragma unroll
-                            for (int it = 0; it < 4; ++it) {
-                                const int item = pt + it * 256, row = item >> 3, c16 = item & 7;
+                            for (int it = 0; it < kDItems; ++it) {
+                                const int item = pt + it * kDP, row = item >> 3, c16 = item & 7;
                                 const size_t at = (size_t)row * 128 + ((c16 ^ (row & 7)) << 4);
                                 *reinterpret_cast<uint4 *>(sa + at) = make_uint4(phi[it][0], phi[it][1], phi[it][2], phi[it][3]);
                                 *reinterpret_cast<uint4 *>(sa + kABytes + at) = make_uint4(plo[it][0], plo[it][1], plo[it][2], plo[it][3]);
@@ -1195,7 +1200,7 @@ int launch_tc(const TcParams &P, int stages, int grid, cudaStream_t st, int stag
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3(DEFORM ? 448u : 320u);
+        cfg.blockDim = dim3(DEFORM ? (unsigned)(192 + kDP) : 320u);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         cudaLaunchAttribute at[1];

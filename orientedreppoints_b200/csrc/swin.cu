@@ -94,6 +94,7 @@ template <> struct Act<true> {
 };
 
 // one warp per token; out may be a padded grid [B,Hp,Wp,C] (rows beyond H,W pre-zeroed by the caller)
+constexpr int kLnChunks = 3;
 template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const typename Act<SPLIT>::T *__restrict__ x, int B, int H, int W, int C, const float *__restrict__ gamma,
@@ -106,11 +107,11 @@ layernorm_kernel(const typename Act<SPLIT>::T *__restrict__ x, int B, int H, int
     const long long tok = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * tpw + lane / G;
     const long long ntok = (long long)B * H * W;
     const bool live = tok < ntok;
-    float v[12][8];                                // C <= 3072: at most 12 chunks per lane
+    float v[kLnChunks][8];                         // C <= 768 (Swin-T's widest stage): at most 3 chunks per lane - few registers, high occupancy
     const int chunks = C >> 3;
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
+    for (int i = 0; i < kLnChunks; ++i) {
         const int ch = g + i * G;
         if (live && ch < chunks) {
             Act<SPLIT>::ld8(x, tok, C, ch * 8, v[i]);
@@ -122,7 +123,7 @@ layernorm_kernel(const typename Act<SPLIT>::T *__restrict__ x, int B, int H, int
     const float mean = s / (float)C;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
+    for (int i = 0; i < kLnChunks; ++i) {
         if (live && g + i * G < chunks) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
@@ -135,7 +136,7 @@ layernorm_kernel(const typename Act<SPLIT>::T *__restrict__ x, int B, int H, int
     const int h = hw / W, w = hw - h * W;
     const long long otok = ((long long)b * Hp + h) * Wp + w;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
+    for (int i = 0; i < kLnChunks; ++i) {
         const int ch = g + i * G;
         if (ch < chunks) {
             const float4 g0 = *reinterpret_cast<const float4 *>(gamma + ch * 8), g1 = *reinterpret_cast<const float4 *>(gamma + ch * 8 + 4);
@@ -322,7 +323,7 @@ template <bool SPLIT>
 static int layernorm_impl(const void *x, int B, int H, int W, int C, const float *gamma, const float *beta, float eps, int Hp, int Wp,
                           void *y, void *stream)
 {
-    if (!x || !y || !gamma || !beta || C < 8 || C > 3072 || (C & 7) || Hp < H || Wp < W) return fail(ORP_EINVAL, "layernorm: C must be a multiple of 8, <= 3072");
+    if (!x || !y || !gamma || !beta || C < 8 || C > 256 * kLnChunks || (C & 7) || Hp < H || Wp < W) return fail(ORP_EINVAL, "layernorm: C must be a multiple of 8, <= 768");
     int rc = ensure_device();
     if (rc) return rc;
     const long long ntok = (long long)B * H * W;

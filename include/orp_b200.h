@@ -384,6 +384,10 @@ int orp_window_attention_bf16(const void *qkv, int B, int H, int W, int Hp, int 
                               const float *bias_table, float scale, void *out, void *stream);
 /* PatchEmbed.proj input rows (4x4 stride 4, :430-441): NCHW fp32 -> bf16 [B,ceil(H/4),ceil(W/4),64], k = c*16+kh*4+kw */
 int orp_patch_embed_rows_bf16(const float *img_nchw, int B, int H, int W, void *out, void *stream);
+/* the same rows from decoded uint8 HWC tiles [B,H,W,3] with the test pipeline's Normalize (to_rgb, (x - mean) * stdinv; mean and stdinv are
+ * HOST arrays of 3 floats) and ImageToTensor fused in (mmdet/datasets/pipelines/transforms.py Normalize, formating.py ImageToTensor) */
+int orp_patch_embed_rows_u8_bf16(const uint8_t *img_hwc, int B, int H, int W, const float *mean, const float *stdinv, int to_rgb,
+                                 void *out, void *stream);
 /* PatchMerging gather (:288-293): [B,H,W,C] -> [B,ceil(H/2),ceil(W/2),4C] */
 int orp_patch_merge_gather_bf16(const void *x, int B, int H, int W, int C, void *y, void *stream);
 /* F.max_pool2d(x, 1, stride=2) (necks/fpn.py:163-165): [B,H,W,C] -> [B,ceil(H/2),ceil(W/2),C] */
@@ -394,6 +398,8 @@ int orp_layernorm_f16x3(const void *x, int B, int H, int W, int C, const float *
 int orp_window_attention_f16x3(const void *qkv, int B, int H, int W, int Hp, int Wp, int C, int heads, int shift,
                                const float *bias_table, float scale, void *out, void *stream);
 int orp_patch_embed_rows_f16x3(const float *img_nchw, int B, int H, int W, void *out, void *stream);
+int orp_patch_embed_rows_u8_f16x3(const uint8_t *img_hwc, int B, int H, int W, const float *mean, const float *stdinv, int to_rgb,
+                                  void *out, void *stream);
 int orp_patch_merge_gather_f16x3(const void *x, int B, int H, int W, int C, void *y, void *stream);
 int orp_subsample2_f16x3(const void *x, int B, int H, int W, int C, void *y, void *stream);
 

@@ -81,12 +81,14 @@ SIGNATURES = {
     "orp_layernorm_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _i, _vp, _vp]),
     "orp_window_attention_bf16": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _vp, _vp]),
     "orp_patch_embed_rows_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "orp_patch_embed_rows_u8_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "orp_patch_merge_gather_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "orp_subsample2_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "orp_stem_conv_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "orp_layernorm_f16x3": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _i, _vp, _vp]),
     "orp_window_attention_f16x3": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _vp, _vp]),
     "orp_patch_embed_rows_f16x3": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "orp_patch_embed_rows_u8_f16x3": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "orp_patch_merge_gather_f16x3": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "orp_subsample2_f16x3": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "orp_stem_im2col_bf16": (_i, [_vp, _i, _i, _i, _vp, _vp]),

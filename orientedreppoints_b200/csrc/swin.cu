@@ -271,6 +271,32 @@ patch_embed_rows_kernel(const float *__restrict__ img, int B, int H, int W, int 
     }
 }
 
+// the same rows straight from decoded uint8 HWC tiles: Normalize (mmdet/datasets/pipelines/transforms.py: to_rgb, (x - mean) / std as
+// (x - mean) * (1 / std), two roundings like the eager expression) + ImageToTensor fused into the gather
+struct NormCfg { float mean[3], stdinv[3]; int to_rgb; };
+template <bool SPLIT>
+__global__ void __launch_bounds__(256)
+patch_embed_rows_u8_kernel(const uint8_t *__restrict__ img, int B, int H, int W, int Ho, int Wo, NormCfg nc,
+                           typename Act<SPLIT>::T *__restrict__ out)
+{
+    const long long total = (long long)B * Ho * Wo * 64;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i & 63);
+        const long long pix = i >> 6;
+        const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+        float v = 0.f;
+        if (k < 48) {
+            const int c = k >> 4, kh = (k >> 2) & 3, kw = k & 3;
+            const int y = oh * 4 + kh, x = ow * 4 + kw;
+            if (y < H && x < W) {
+                const float raw = (float)img[(((long long)b * H + y) * W + x) * 3 + (nc.to_rgb ? 2 - c : c)];
+                v = __fmul_rn(__fsub_rn(raw, nc.mean[c]), nc.stdinv[c]);
+            }
+        }
+        Act<SPLIT>::st(out, pix, 64, k, v);
+    }
+}
+
 // PatchMerging gather (:288-293): [B,H,W,C] -> [B,ceil(H/2),ceil(W/2),4C] = x(0::2,0::2) | x(1::2,0::2) | x(0::2,1::2) | x(1::2,1::2)
 // (16-bit elements of either format; P = planes per token: 1 bf16, 2 split - the hi and lo planes are gathered alike)
 __global__ void __launch_bounds__(256)
@@ -392,6 +418,33 @@ extern "C" int orp_patch_embed_rows_bf16(const float *img_nchw, int B, int H, in
 extern "C" int orp_patch_embed_rows_f16x3(const float *img_nchw, int B, int H, int W, void *out, void *stream)
 {
     return patch_embed_rows_impl<true>(img_nchw, B, H, W, out, stream);
+}
+
+template <bool SPLIT>
+static int patch_embed_rows_u8_impl(const uint8_t *img_hwc, int B, int H, int W, const float *mean, const float *stdinv, int to_rgb,
+                                    void *out, void *stream)
+{
+    if (!img_hwc || !out || !mean || !stdinv) return fail(ORP_EINVAL, "patch_embed_rows_u8: bad arguments");
+    int rc = ensure_device();
+    if (rc) return rc;
+    NormCfg nc;
+    for (int c = 0; c < 3; ++c) { nc.mean[c] = mean[c]; nc.stdinv[c] = stdinv[c]; }
+    nc.to_rgb = to_rgb ? 1 : 0;
+    const int Ho = (H + 3) / 4, Wo = (W + 3) / 4;
+    patch_embed_rows_u8_kernel<SPLIT><<<grid_for((long long)B * Ho * Wo * 64, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        img_hwc, B, H, W, Ho, Wo, nc, static_cast<typename Act<SPLIT>::T *>(out));
+    ORP_LAUNCHED();
+    return ORP_OK;
+}
+extern "C" int orp_patch_embed_rows_u8_bf16(const uint8_t *img_hwc, int B, int H, int W, const float *mean, const float *stdinv,
+                                            int to_rgb, void *out, void *stream)
+{
+    return patch_embed_rows_u8_impl<false>(img_hwc, B, H, W, mean, stdinv, to_rgb, out, stream);
+}
+extern "C" int orp_patch_embed_rows_u8_f16x3(const uint8_t *img_hwc, int B, int H, int W, const float *mean, const float *stdinv,
+                                             int to_rgb, void *out, void *stream)
+{
+    return patch_embed_rows_u8_impl<true>(img_hwc, B, H, W, mean, stdinv, to_rgb, out, stream);
 }
 
 static int patch_merge_gather_impl(const void *x, int B, int H, int W, int C, int P, void *y, void *stream)

@@ -223,8 +223,8 @@ class OrientedRepPointsDetector:
     def extract_feat(self, img):
         e = self.eng
         if self.depth == "swin_tiny":
-            img = self.normalize(img)
-            c3, c4, c5 = self.swin.forward(img)
+            # decoded uint8 tiles: Normalize + ImageToTensor are fused into the patch gather
+            c3, c4, c5 = self.swin.forward(img, self.img_norm_cfg)
             l2 = e.conv_gn(c5, *self.lat[2])
             l1 = e.conv_gn(c4, *self.lat[1], up=l2)
             l0 = e.conv_gn(c3, *self.lat[0], up=l1)

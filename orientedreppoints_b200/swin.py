@@ -100,6 +100,7 @@ class SwinTiny:
                 self.merges.append(dict(norm=_LN(sd, "backbone.layers.%d.downsample.norm" % i, device),
                                         red=_linear(sd, "backbone.layers.%d.downsample.reduction" % i, device)))
         self.out_norms = {i: _LN(sd, "backbone.norm%d" % i, device) for i in (1, 2, 3)}
+        self._padded = {}
 
     # ------------------------------------------------------------------ primitive launches
     # (the engine decides the activation format: bf16 [B,H,W,C] or split fp16 [B,H,W,2,C]; `e.suffix` picks the entry points)
@@ -109,7 +110,15 @@ class SwinTiny:
     def _ln(self, x, norm, hp=None, wp=None):
         b, h, w, c = self.e.dims(x)
         hp, wp = hp or h, wp or w
-        y = self.e.alloc(b, hp, wp, c, zero=(hp, wp) != (h, w))                            # F.pad zeros after norm1
+        if (hp, wp) != (h, w):
+            # F.pad zeros after norm1: the kernel writes the H x W interior only, so one zero-filled buffer per shape is
+            # reused by every block of the stage (its consumer, the qkv projection, is stream-ordered before the next norm1)
+            key = (b, h, w, hp, wp, c)
+            y = self._padded.get(key)
+            if y is None:
+                y = self._padded[key] = self.e.alloc(b, hp, wp, c, zero=True)
+        else:
+            y = self.e.alloc(b, hp, wp, c)
         _lib.check(self._fn("layernorm")(_lib.ptr(x), b, h, w, c, _lib.ptr(norm.gamma), _lib.ptr(norm.beta), 1e-5, hp, wp,
                                          _lib.ptr(y), _lib.current_stream_ptr()), "orp_layernorm")
         return y
@@ -143,13 +152,26 @@ class SwinTiny:
                    "orp_patch_merge_gather")
         return self.e.conv(self._ln(g, m["norm"]), m["red"])
 
-    def forward(self, img):
-        img = img.to(self.dev, torch.float32).contiguous()
-        b, _, h, w = img.shape
-        ho, wo = (h + 3) // 4, (w + 3) // 4
-        rows = self.e.alloc(b, ho, wo, 64)
-        _lib.check(self._fn("patch_embed_rows")(_lib.ptr(img), b, h, w, _lib.ptr(rows), _lib.current_stream_ptr()),
-                   "orp_patch_embed_rows")
+    def forward(self, img, img_norm_cfg=None):
+        """img: normalised float NCHW, or decoded uint8 HWC tiles [B,H,W,3] together with the pipeline's img_norm_cfg (Normalize +
+        ImageToTensor are then fused into the patch gather)"""
+        if img.dtype == torch.uint8:
+            import ctypes
+            img = img.to(self.dev).contiguous()
+            b, h, w, _ = img.shape
+            mean = (ctypes.c_float * 3)(*[float(v) for v in img_norm_cfg["mean"]])
+            stdinv = (ctypes.c_float * 3)(*[1.0 / float(v) for v in img_norm_cfg["std"]])      # rounded to fp32 as detector.normalize does
+            ho, wo = (h + 3) // 4, (w + 3) // 4
+            rows = self.e.alloc(b, ho, wo, 64)
+            _lib.check(self._fn("patch_embed_rows_u8")(_lib.ptr(img), b, h, w, mean, stdinv, 1 if img_norm_cfg.get("to_rgb", True) else 0,
+                                                      _lib.ptr(rows), _lib.current_stream_ptr()), "orp_patch_embed_rows_u8")
+        else:
+            img = img.to(self.dev, torch.float32).contiguous()
+            b, _, h, w = img.shape
+            ho, wo = (h + 3) // 4, (w + 3) // 4
+            rows = self.e.alloc(b, ho, wo, 64)
+            _lib.check(self._fn("patch_embed_rows")(_lib.ptr(img), b, h, w, _lib.ptr(rows), _lib.current_stream_ptr()),
+                       "orp_patch_embed_rows")
         x = self._ln(self.e.conv(rows, self.embed), self.embed_norm)
         outs = []
         for i, stage in enumerate(self.blocks):

@@ -160,3 +160,16 @@ def test_swin_f16x3_kernels_and_backbone_vs_fp64(cuda, swin_sd):
     assert e.overflow_count() == 0
     res = det.simple_test(img)
     assert len(res) == 2 and len(res[0]) == 15
+
+
+@pytest.mark.parametrize("precision", ["bf16", "f16x3"])
+def test_swin_uint8_tiles_equal_normalized_float_input(cuda, swin_sd, precision):
+    """decoded uint8 HWC tiles through the fused Normalize + patch gather == the pipeline's Normalize / ImageToTensor done with
+    torch ops followed by the float entry point: identical bits (same two fp32 roundings per pixel)"""
+    from orientedreppoints_b200.detector import OrientedRepPointsDetector
+    det = OrientedRepPointsDetector(swin_sd, "swin_tiny", cuda, precision, test_cfg=dict(score_thr=0.02))
+    u8 = torch.randint(0, 256, (2, 122, 95, 3), generator=torch.Generator().manual_seed(5), dtype=torch.uint8).to(cuda)
+    fa = det.swin.forward(u8, det.img_norm_cfg)
+    fb = det.swin.forward(det.normalize(u8))
+    for a, b in zip(fa, fb):
+        assert torch.equal(det.eng.to_float(a), det.eng.to_float(b))

@@ -94,20 +94,19 @@ template <> struct Act<true> {
 };
 
 // one warp per token; out may be a padded grid [B,Hp,Wp,C] (rows beyond H,W pre-zeroed by the caller)
-constexpr int kLnChunks = 3;
-template <bool SPLIT>
+template <bool SPLIT, int kLnChunks>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const typename Act<SPLIT>::T *__restrict__ x, int B, int H, int W, int C, const float *__restrict__ gamma,
                  const float *__restrict__ beta, float eps, int Hp, int Wp, int G, typename Act<SPLIT>::T *__restrict__ y)
 {
-    // a group of G lanes (G = power of two >= C / 8, at most 32) per token, 32 / G tokens per warp; a lane owns the 16-byte chunks
-    // (8 channels) g, g + G, ... of its token: vector loads and stores, all lanes busy for the narrow stages (C = 96: G = 16)
+    // a group of G lanes (a power of two, G * kLnChunks >= C / 8) per token, 32 / G tokens per warp; a lane owns the 16-byte chunks
+    // (8 channels) g, g + G, ... of its token: vector loads and stores, all lanes busy (C = 96: 4 lanes x 3 chunks, 8 tokens per warp)
     const int lane = threadIdx.x & 31, g = lane & (G - 1);
     const int tpw = 32 / G;                                                    // tokens per warp
     const long long tok = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * tpw + lane / G;
     const long long ntok = (long long)B * H * W;
     const bool live = tok < ntok;
-    float v[kLnChunks][8];                         // C <= 768 (Swin-T's widest stage): at most 3 chunks per lane - few registers, high occupancy
+    float v[kLnChunks][8];                         // 3 chunks per lane up to C = 768 (every block norm of Swin-T: few registers, high occupancy), 6 for the 1536-wide PatchMerging norm
     const int chunks = C >> 3;
     float s = 0.f;
 #pragma unroll
@@ -251,6 +250,206 @@ window_attention_kernel(const typename Act<SPLIT>::T *__restrict__ qkv, int B, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Window attention on the tensor cores (warp-level mma.sync m16n8k16, fp32 accumulation).  One block of four warps per
+// (window, head); warp w owns query rows 16 w .. 16 w + 15 of the window's 49 (padded to 64).  Q, K, V are staged as the 16-bit
+// planes they are stored in (fp16 hi / lo in split mode, bf16 otherwise) - no conversion; S = Q K^T and O = P V are evaluated
+// with the same three-term products as the convolutions (lo x hi, hi x lo, hi x hi), the probabilities P are split into a
+// (hi, lo) pair in registers (both modes), bias + region mask + softmax run on the accumulator fragments in fp32.
+// ---------------------------------------------------------------------------------------------
+constexpr int kAS = 40;            // shared-memory row pitch in 16-bit elements (80 B: conflict-free ldmatrix rows)
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void *p)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void *p)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+template <bool SPLIT>
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    if (SPLIT)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (x, y) -> packed 16-bit pair of the engine's format and the packed remainder pair
+template <bool SPLIT>
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t &hi, uint32_t &lo)
+{
+    if (SPLIT) {
+        const __half2 h = __floats2half2_rn(x, y);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+        hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
+    } else {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+        const float2 hf = __bfloat1622float2(h);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(x - hf.x, y - hf.y);
+        hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
+    }
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(128)
+window_attention_mma_kernel(const typename Act<SPLIT>::T *__restrict__ qkv, int B, int H, int W, int Hp, int Wp, int C, int heads,
+                            int shift, const float *__restrict__ bias_table /* [169, heads] */, float scale,
+                            typename Act<SPLIT>::T *__restrict__ out)
+{
+    constexpr int NP = SPLIT ? 2 : 1;                      // 16-bit planes per value
+    __shared__ __align__(16) uint16_t sq[NP][64][kAS], sk[NP][64][kAS], sv[NP][64][kAS];
+    __shared__ int s_src[64], s_reg[64];
+    __shared__ float s_bias[169];
+    const int nww = Wp / kWin, nwh = Hp / kWin;
+    const int head = blockIdx.y;
+    const int wid = blockIdx.x % (nwh * nww), b = blockIdx.x / (nwh * nww);
+    const int wy = wid / nww, wx = wid - wy * nww;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 64) {
+        int src = 0, reg = 0;
+        if (tid < kTok) {
+            const int ty = tid / kWin, tx = tid - ty * kWin;
+            const int ys = wy * kWin + ty, xs = wx * kWin + tx;                 // coordinates in the shifted frame
+            int yo = ys + shift, xo = xs + shift;                                // roll(x, -shift): shifted[y] = x[(y + shift) % Hp]
+            if (yo >= Hp) yo -= Hp;
+            if (xo >= Wp) xo -= Wp;
+            src = (b * Hp + yo) * Wp + xo;
+            // BasicLayer mask regions (:376-387): slices (0,-7), (-7,-3), (-3,None) of the shifted frame
+            const int hr = ys < Hp - kWin ? 0 : (ys < Hp - shift ? 1 : 2);
+            const int wr = xs < Wp - kWin ? 0 : (xs < Wp - shift ? 1 : 2);
+            reg = shift > 0 ? hr * 3 + wr : 0;
+        }
+        s_src[tid] = src;
+        s_reg[tid] = reg;
+    }
+    for (int i = tid; i < 169; i += 128) s_bias[i] = bias_table[i * heads + head];
+    __syncthreads();
+    // stage the 16-byte chunks of q | k | v (both planes); rows 49..63 are zero
+    for (int e = tid; e < 64 * 3 * NP * 4; e += 128) {
+        const int c4 = e & 3, pl = (e >> 2) % NP, ten = (e / (4 * NP)) % 3, j = e / (12 * NP);
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (j < kTok) {
+            const uint16_t *src = reinterpret_cast<const uint16_t *>(qkv) + ((size_t)s_src[j] * NP + pl) * (size_t)(3 * C) + ten * C + head * kHd + c4 * 8;
+            val = *reinterpret_cast<const uint4 *>(src);
+        }
+        uint16_t *dst = (ten == 0 ? &sq[pl][j][0] : ten == 1 ? &sk[pl][j][0] : &sv[pl][j][0]) + c4 * 8;
+        *reinterpret_cast<uint4 *>(dst) = val;
+    }
+    __syncthreads();
+    if (warp * 16 >= kTok) return;                         // (never: 4 warps cover rows 0..63, row 48 lives in warp 3)
+    const int g = lane >> 2, t4 = lane & 3, m0 = warp * 16;
+
+    // ---- S = Q K^T (accumulator fragment: [0],[1] = row g, cols 2 t4, +1; [2],[3] = row g + 8)
+    uint32_t aq[NP][2][4];
+#pragma unroll
+    for (int pl = 0; pl < NP; ++pl)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ldsm_x4(aq[pl][ks], &sq[pl][m0 + (lane & 15)][ks * 16 + (lane >> 4) * 8]);
+    float sc[8][4];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+        uint32_t bk[NP][4];
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl) ldsm_x4(bk[pl], &sk[pl][8 * j + (lane & 7)][(lane >> 3) * 8]);
+        if (SPLIT) {
+            mma16816<SPLIT>(sc[j], aq[NP - 1][0], bk[0][0], bk[0][1]); mma16816<SPLIT>(sc[j], aq[NP - 1][1], bk[0][2], bk[0][3]);      // q_lo k_hi
+            mma16816<SPLIT>(sc[j], aq[0][0], bk[NP - 1][0], bk[NP - 1][1]); mma16816<SPLIT>(sc[j], aq[0][1], bk[NP - 1][2], bk[NP - 1][3]);   // q_hi k_lo
+        }
+        mma16816<SPLIT>(sc[j], aq[0][0], bk[0][0], bk[0][1]); mma16816<SPLIT>(sc[j], aq[0][1], bk[0][2], bk[0][3]);
+    }
+    // ---- q * scale (:138), + relative position bias (:107-118, :141-144), + region mask (:388-389), softmax over the 49 keys
+    const int r0 = m0 + g, r1 = r0 + 8;
+    const int q0 = r0 < kTok ? r0 : kTok - 1, q1 = r1 < kTok ? r1 : kTok - 1;     // padded rows compute on a clamped query, never stored
+    const int ty0 = q0 / kWin, tx0 = q0 - ty0 * kWin, ty1 = q1 / kWin, tx1 = q1 - ty1 * kWin;
+    const int rg0 = s_reg[q0], rg1 = s_reg[q1];
+    float mx0 = -3.0e38f, mx1 = -3.0e38f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int c = 8 * j + 2 * t4 + u;
+            if (c < kTok) {
+                const int jy = c / kWin, jx = c - jy * kWin;
+                const int rc = s_reg[c];
+                float a0 = sc[j][u] * scale + s_bias[(ty0 - jy + kWin - 1) * (2 * kWin - 1) + (tx0 - jx + kWin - 1)];
+                float a1 = sc[j][2 + u] * scale + s_bias[(ty1 - jy + kWin - 1) * (2 * kWin - 1) + (tx1 - jx + kWin - 1)];
+                if (rg0 != rc) a0 += -100.0f;
+                if (rg1 != rc) a1 += -100.0f;
+                sc[j][u] = a0; sc[j][2 + u] = a1;
+                mx0 = fmaxf(mx0, a0); mx1 = fmaxf(mx1, a1);
+            } else {
+                sc[j][u] = -3.0e38f; sc[j][2 + u] = -3.0e38f;
+            }
+        }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float den0 = 0.f, den1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const bool in = (8 * j + 2 * t4 + u) < kTok;
+            const float e0 = in ? expf(sc[j][u] - mx0) : 0.f, e1 = in ? expf(sc[j][2 + u] - mx1) : 0.f;
+            sc[j][u] = e0; sc[j][2 + u] = e1;
+            den0 += e0; den1 += e1;
+        }
+    den0 += __shfl_xor_sync(0xffffffffu, den0, 1); den0 += __shfl_xor_sync(0xffffffffu, den0, 2);
+    den1 += __shfl_xor_sync(0xffffffffu, den1, 1); den1 += __shfl_xor_sync(0xffffffffu, den1, 2);
+    const float inv0 = 1.0f / den0, inv1 = 1.0f / den1;
+    sc[7][0] = sc[7][1] = sc[7][2] = sc[7][3] = 0.f;       // keys 56..63 do not exist
+
+    // ---- O = P V: the accumulator fragments of two neighbouring key tiles are the A fragment of one 16-key step
+    float o[4][4];
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn) o[jn][0] = o[jn][1] = o[jn][2] = o[jn][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        uint32_t ph[4], pl_[4];
+        split_pair<SPLIT>(sc[2 * kk][0] * inv0, sc[2 * kk][1] * inv0, ph[0], pl_[0]);
+        split_pair<SPLIT>(sc[2 * kk][2] * inv1, sc[2 * kk][3] * inv1, ph[1], pl_[1]);
+        split_pair<SPLIT>(sc[2 * kk + 1][0] * inv0, sc[2 * kk + 1][1] * inv0, ph[2], pl_[2]);
+        split_pair<SPLIT>(sc[2 * kk + 1][2] * inv1, sc[2 * kk + 1][3] * inv1, ph[3], pl_[3]);
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+            uint32_t bv[NP][4];
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl)
+                ldsm_x4_trans(bv[pl], &sv[pl][16 * kk + ((lane >> 3) & 1) * 8 + (lane & 7)][16 * np + (lane >> 4) * 8]);
+            mma16816<SPLIT>(o[2 * np], pl_, bv[0][0], bv[0][1]); mma16816<SPLIT>(o[2 * np + 1], pl_, bv[0][2], bv[0][3]);              // p_lo v_hi
+            if (SPLIT) { mma16816<SPLIT>(o[2 * np], ph, bv[NP - 1][0], bv[NP - 1][1]); mma16816<SPLIT>(o[2 * np + 1], ph, bv[NP - 1][2], bv[NP - 1][3]); }   // p_hi v_lo
+            mma16816<SPLIT>(o[2 * np], ph, bv[0][0], bv[0][1]); mma16816<SPLIT>(o[2 * np + 1], ph, bv[0][2], bv[0][3]);
+        }
+    }
+    // ---- window_reverse + roll(+shift) + crop: a token returns to its original position if that is inside H x W
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int r = half ? r1 : r0;
+        if (r >= kTok) continue;
+        const int src = s_src[r];
+        const int xo = src % Wp, yo = (src / Wp) % Hp;
+        if (yo >= H || xo >= W) continue;
+        const long long otok = ((long long)b * H + yo) * W + xo;
+        uint16_t *dst = reinterpret_cast<uint16_t *>(out) + (size_t)otok * NP * C + head * kHd + 2 * t4;
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) {
+            float x = o[jn][2 * half], y = o[jn][2 * half + 1];
+            uint32_t hi, lo;
+            if (SPLIT) { x = fminf(fmaxf(x, -65504.f), 65504.f); y = fminf(fmaxf(y, -65504.f), 65504.f); }
+            split_pair<SPLIT>(x, y, hi, lo);
+            *reinterpret_cast<uint32_t *>(dst + 8 * jn) = hi;
+            if (SPLIT) *reinterpret_cast<uint32_t *>(dst + C + 8 * jn) = lo;
+        }
+    }
+}
+
 // PatchEmbed.proj input rows: NCHW fp32 image -> bf16 [B, ceil(H/4), ceil(W/4), 64], k = c*16 + kh*4 + kw (< 48), zero padded
 template <bool SPLIT>
 __global__ void __launch_bounds__(256)
@@ -349,16 +548,24 @@ template <bool SPLIT>
 static int layernorm_impl(const void *x, int B, int H, int W, int C, const float *gamma, const float *beta, float eps, int Hp, int Wp,
                           void *y, void *stream)
 {
-    if (!x || !y || !gamma || !beta || C < 8 || C > 256 * kLnChunks || (C & 7) || Hp < H || Wp < W) return fail(ORP_EINVAL, "layernorm: C must be a multiple of 8, <= 768");
+    if (!x || !y || !gamma || !beta || C < 8 || C > 1536 || (C & 7) || Hp < H || Wp < W) return fail(ORP_EINVAL, "layernorm: C must be a multiple of 8, <= 1536");
     int rc = ensure_device();
     if (rc) return rc;
     const long long ntok = (long long)B * H * W;
     typedef typename Act<SPLIT>::T T;
+    // lanes per token: the smallest power of two whose lanes hold the token in at most kLnChunks 16-byte chunks each - for Swin-T's
+    // widths (96 / 192 / 384 / 768 -> 4 / 8 / 16 / 32 lanes x 3 chunks) no lane idles
+    const int kLnChunks = C <= 768 ? 3 : 6;
     int G = 1;
-    while (G < 32 && G < (C >> 3)) G <<= 1;
+    while (G < 32 && G * kLnChunks < (C >> 3)) G <<= 1;
     const long long tok_per_block = 8LL * (32 / G);
-    layernorm_kernel<SPLIT><<<(unsigned)((ntok + tok_per_block - 1) / tok_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const T *>(x), B, H, W, C, gamma, beta, eps, Hp, Wp, G, static_cast<T *>(y));
+    const unsigned nblk = (unsigned)((ntok + tok_per_block - 1) / tok_per_block);
+    if (kLnChunks == 3)
+        layernorm_kernel<SPLIT, 3><<<nblk, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const T *>(x), B, H, W, C, gamma, beta, eps,
+                                                                                        Hp, Wp, G, static_cast<T *>(y));
+    else
+        layernorm_kernel<SPLIT, 6><<<nblk, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const T *>(x), B, H, W, C, gamma, beta, eps,
+                                                                                        Hp, Wp, G, static_cast<T *>(y));
     ORP_LAUNCHED();
     return ORP_OK;
 }
@@ -383,8 +590,13 @@ static int window_attention_impl(const void *qkv, int B, int H, int W, int Hp, i
     if (rc) return rc;
     dim3 grid(B * (Hp / kWin) * (Wp / kWin), heads);
     typedef typename Act<SPLIT>::T T;
-    window_attention_kernel<SPLIT><<<grid, 64, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const T *>(qkv), B, H, W, Hp, Wp, C, heads, shift, bias_table, scale, static_cast<T *>(out));
+    static const bool simt = getenv("ORP_SWIN_ATTN_SIMT") != nullptr;      // experiments: the CUDA-core kernel of round 1
+    if (simt)
+        window_attention_kernel<SPLIT><<<grid, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const T *>(qkv), B, H, W, Hp, Wp, C, heads, shift, bias_table, scale, static_cast<T *>(out));
+    else
+        window_attention_mma_kernel<SPLIT><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const T *>(qkv), B, H, W, Hp, Wp, C, heads, shift, bias_table, scale, static_cast<T *>(out));
     ORP_LAUNCHED();
     return ORP_OK;
 }

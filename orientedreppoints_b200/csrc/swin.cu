@@ -331,15 +331,26 @@ window_attention_mma_kernel(const typename Act<SPLIT>::T *__restrict__ qkv, int 
     for (int i = tid; i < 169; i += 128) s_bias[i] = bias_table[i * heads + head];
     __syncthreads();
     // stage the 16-byte chunks of q | k | v (both planes); rows 49..63 are zero
-    for (int e = tid; e < 64 * 3 * NP * 4; e += 128) {
-        const int c4 = e & 3, pl = (e >> 2) % NP, ten = (e / (4 * NP)) % 3, j = e / (12 * NP);
-        uint4 val = make_uint4(0u, 0u, 0u, 0u);
-        if (j < kTok) {
-            const uint16_t *src = reinterpret_cast<const uint16_t *>(qkv) + ((size_t)s_src[j] * NP + pl) * (size_t)(3 * C) + ten * C + head * kHd + c4 * 8;
-            val = *reinterpret_cast<const uint4 *>(src);
+    {
+        constexpr int kIt = 64 * 3 * NP * 4 / 128;          // 16-byte chunks per thread: all loads in flight before the first store
+        uint4 val[kIt];
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int e = tid + it * 128;
+            const int c4 = e & 3, pl = (e >> 2) % NP, ten = (e / (4 * NP)) % 3, j = e / (12 * NP);
+            val[it] = make_uint4(0u, 0u, 0u, 0u);
+            if (j < kTok) {
+                const uint16_t *src = reinterpret_cast<const uint16_t *>(qkv) + ((size_t)s_src[j] * NP + pl) * (size_t)(3 * C) + ten * C + head * kHd + c4 * 8;
+                val[it] = *reinterpret_cast<const uint4 *>(src);
+            }
         }
-        uint16_t *dst = (ten == 0 ? &sq[pl][j][0] : ten == 1 ? &sk[pl][j][0] : &sv[pl][j][0]) + c4 * 8;
-        *reinterpret_cast<uint4 *>(dst) = val;
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int e = tid + it * 128;
+            const int c4 = e & 3, pl = (e >> 2) % NP, ten = (e / (4 * NP)) % 3, j = e / (12 * NP);
+            uint16_t *dst = (ten == 0 ? &sq[pl][j][0] : ten == 1 ? &sk[pl][j][0] : &sv[pl][j][0]) + c4 * 8;
+            *reinterpret_cast<uint4 *>(dst) = val[it];
+        }
     }
     __syncthreads();
     if (warp * 16 >= kTok) return;                         // (never: 4 warps cover rows 0..63, row 48 lives in warp 3)

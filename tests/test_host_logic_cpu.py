@@ -93,3 +93,14 @@ def test_host_helpers_against_reference_golden():
     mb, ms = D.merge_aug_results(_Self(), [torch.from_numpy(g[k]) for k in ("m_b1", "m_b2", "m_b3")],
                                  [torch.from_numpy(g[k]) for k in ("m_s1", "m_s2", "m_s3")], metas)
     assert np.array_equal(mb.numpy(), g["m_out_b"]) and np.array_equal(ms.numpy(), g["m_out_s"])
+
+
+def test_f16x3_weight_row_padding_rule():
+    """output columns the tensor-core kernel computes per layer (engine_tc.EngineTCSplit._pad_cout): power-of-two widths of the
+    ResNets unchanged, small fp32 heads in 32s, Swin's 192-channel layers as ONE 256-wide tile, everything else in 64s"""
+    from orientedreppoints_b200.engine_tc import EngineTCSplit as E
+    want = {15: 32, 18: 32, 32: 32, 64: 64, 96: 128, 128: 128, 192: 256, 256: 256, 288: 320, 384: 384, 512: 512, 576: 576,
+            768: 768, 1024: 1024, 1152: 1152, 2048: 2048}
+    for cout, p in want.items():
+        assert E._pad_cout(cout) == p, cout
+        assert p >= cout and (p % 32 == 0)

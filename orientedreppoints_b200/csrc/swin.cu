@@ -304,7 +304,7 @@ window_attention_mma_kernel(const typename Act<SPLIT>::T *__restrict__ qkv, int 
 {
     constexpr int NP = SPLIT ? 2 : 1;                      // 16-bit planes per value
     __shared__ __align__(16) uint16_t sq[NP][64][kAS], sk[NP][64][kAS], sv[NP][64][kAS];
-    __shared__ int s_src[64], s_reg[64];
+    __shared__ int s_src[64], s_reg[64], s_col[64];
     __shared__ float s_bias[169];
     const int nww = Wp / kWin, nwh = Hp / kWin;
     const int head = blockIdx.y;
@@ -313,6 +313,10 @@ window_attention_mma_kernel(const typename Act<SPLIT>::T *__restrict__ qkv, int 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 64) {
         int src = 0, reg = 0;
+        // relative position index (:107-118) = (ty - jy + 6) * 13 + (tx - jx + 6) = [ty * 13 + tx + 84] - [jy * 13 + jx]: one table entry
+        // per token, the softmax loop subtracts
+        const int tq = tid < kTok ? tid : kTok - 1;
+        s_col[tid] = (tq / kWin) * (2 * kWin - 1) + (tq % kWin);
         if (tid < kTok) {
             const int ty = tid / kWin, tx = tid - ty * kWin;
             const int ys = wy * kWin + ty, xs = wx * kWin + tx;                 // coordinates in the shifted frame
@@ -378,7 +382,7 @@ window_attention_mma_kernel(const typename Act<SPLIT>::T *__restrict__ qkv, int 
     // ---- q * scale (:138), + relative position bias (:107-118, :141-144), + region mask (:388-389), softmax over the 49 keys
     const int r0 = m0 + g, r1 = r0 + 8;
     const int q0 = r0 < kTok ? r0 : kTok - 1, q1 = r1 < kTok ? r1 : kTok - 1;     // padded rows compute on a clamped query, never stored
-    const int ty0 = q0 / kWin, tx0 = q0 - ty0 * kWin, ty1 = q1 / kWin, tx1 = q1 - ty1 * kWin;
+    const int rp0 = s_col[q0] + (kWin - 1) * (2 * kWin - 1) + (kWin - 1), rp1 = s_col[q1] + (kWin - 1) * (2 * kWin - 1) + (kWin - 1);
     const int rg0 = s_reg[q0], rg1 = s_reg[q1];
     float mx0 = -3.0e38f, mx1 = -3.0e38f;
 #pragma unroll
@@ -387,10 +391,9 @@ window_attention_mma_kernel(const typename Act<SPLIT>::T *__restrict__ qkv, int 
         for (int u = 0; u < 2; ++u) {
             const int c = 8 * j + 2 * t4 + u;
             if (c < kTok) {
-                const int jy = c / kWin, jx = c - jy * kWin;
-                const int rc = s_reg[c];
-                float a0 = sc[j][u] * scale + s_bias[(ty0 - jy + kWin - 1) * (2 * kWin - 1) + (tx0 - jx + kWin - 1)];
-                float a1 = sc[j][2 + u] * scale + s_bias[(ty1 - jy + kWin - 1) * (2 * kWin - 1) + (tx1 - jx + kWin - 1)];
+                const int cp = s_col[c], rc = s_reg[c];
+                float a0 = fmaf(sc[j][u], scale, s_bias[rp0 - cp]);
+                float a1 = fmaf(sc[j][2 + u], scale, s_bias[rp1 - cp]);
                 if (rg0 != rc) a0 += -100.0f;
                 if (rg1 != rc) a1 += -100.0f;
                 sc[j][u] = a0; sc[j][2 + u] = a1;

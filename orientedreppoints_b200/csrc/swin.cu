@@ -336,24 +336,26 @@ window_attention_mma_kernel(const typename Act<SPLIT>::T *__restrict__ qkv, int 
     __syncthreads();
     // stage the 16-byte chunks of q | k | v (both planes); rows 49..63 are zero
     {
-        constexpr int kIt = 64 * 3 * NP * 4 / 128;          // 16-byte chunks per thread: all loads in flight before the first store
-        uint4 val[kIt];
+        // thread -> (16-byte chunk c4, plane pl) fixed, rows j = jb + kRows * i, tensor q | k | v: simple addressing, all loads in
+        // flight before the first store
+        constexpr int kRows = 128 / (4 * NP);                // rows covered by one pass of the block
+        constexpr int kRowIt = 64 / kRows;
+        const int c4 = tid & 3, pl = (tid >> 2) % NP, jb = tid / (4 * NP);
+        uint4 val[kRowIt][3];
 #pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-            const int e = tid + it * 128;
-            const int c4 = e & 3, pl = (e >> 2) % NP, ten = (e / (4 * NP)) % 3, j = e / (12 * NP);
-            val[it] = make_uint4(0u, 0u, 0u, 0u);
-            if (j < kTok) {
-                const uint16_t *src = reinterpret_cast<const uint16_t *>(qkv) + ((size_t)s_src[j] * NP + pl) * (size_t)(3 * C) + ten * C + head * kHd + c4 * 8;
-                val[it] = *reinterpret_cast<const uint4 *>(src);
-            }
+        for (int i = 0; i < kRowIt; ++i) {
+            const int j = jb + kRows * i;
+            const uint16_t *src = reinterpret_cast<const uint16_t *>(qkv) + ((size_t)s_src[j] * NP + pl) * (size_t)(3 * C) + head * kHd + c4 * 8;
+#pragma unroll
+            for (int ten = 0; ten < 3; ++ten)
+                val[i][ten] = j < kTok ? *reinterpret_cast<const uint4 *>(src + ten * C) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-            const int e = tid + it * 128;
-            const int c4 = e & 3, pl = (e >> 2) % NP, ten = (e / (4 * NP)) % 3, j = e / (12 * NP);
-            uint16_t *dst = (ten == 0 ? &sq[pl][j][0] : ten == 1 ? &sk[pl][j][0] : &sv[pl][j][0]) + c4 * 8;
-            *reinterpret_cast<uint4 *>(dst) = val[it];
+        for (int i = 0; i < kRowIt; ++i) {
+            const int j = jb + kRows * i;
+            *reinterpret_cast<uint4 *>(&sq[pl][j][c4 * 8]) = val[i][0];
+            *reinterpret_cast<uint4 *>(&sk[pl][j][c4 * 8]) = val[i][1];
+            *reinterpret_cast<uint4 *>(&sv[pl][j][c4 * 8]) = val[i][2];
         }
     }
     __syncthreads();
